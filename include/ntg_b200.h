@@ -1,0 +1,215 @@
+/*
+ * ntg_b200.h -- C ABI of the B200-native batched collocation evaluator.
+ *
+ * This is the drop-in boundary for NTG's per-iterate hot path: everything
+ * NPSOL's funobj/funcon callbacks compute in the reference
+ * (src/ntg.c:274-371 and the cost/constraint/colloc/integrator/matrix code
+ * under them), for P independent coefficient vectors in one launch.
+ *
+ * Plain C: pointers and sizes only, no torch / C++ types.  Device pointers are
+ * ordinary CUDA device addresses; `stream` is a cudaStream_t passed as void*.
+ *
+ * Every entry point returns 0 on success or a negative NTGB_E* code;
+ * ntgb_last_error() gives the message of the last failure on this thread.
+ * There is no CPU fallback: without a CUDA device every compute entry fails
+ * with NTGB_ECUDA.
+ */
+#ifndef NTG_B200_H_
+#define NTG_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- active variables: identical to reference src/av.h:18-26 ------------- */
+#ifndef _AV_H_
+#define _AV_H_
+#define AVINITIAL    0
+#define AVTRAJECTORY 1
+#define AVFINAL      2
+typedef struct AVStruct {
+    int output;
+    int deriv;
+} AV;
+#endif
+
+/* ---- callback surface: reference src/ntg.c:34-41, src/ntg.h:81-92 -------- */
+typedef void (*ntg_nlicf_t)(int *mode, int *nstate, double *f, double **df, double **zp);
+typedef void (*ntg_nltcf_t)(int *mode, int *nstate, int *i, double *f, double **df, double **zp);
+typedef void (*ntg_nlfcf_t)(int *mode, int *nstate, double *f, double **df, double **zp);
+typedef void (*ntg_icf_t)(int *mode, int *nstate, double *f, double *df, double **zp);
+typedef void (*ntg_ucf_t)(int *mode, int *nstate, int *i, double *f, double *df, double **zp);
+typedef void (*ntg_fcf_t)(int *mode, int *nstate, double *f, double *df, double **zp);
+
+/*
+ * Problem description = the setup subset of ntg()'s arguments, same names,
+ * same meaning, same order (reference src/ntg.h:72-99, src/ntg.c:54-83).
+ * Callbacks are the HOST addresses of functions that were also compiled as
+ * device code in a registered callback pack (see ntgb_register_pack).
+ */
+typedef struct ntgb_setup {
+    int nout;
+    const double *bps;
+    int nbps;
+    const int *kninterv;
+    const double *const *knots;
+    const int *order;
+    const int *mult;
+    const int *maxderiv;
+
+    int nlic; const double *const *lic;
+    int nltc; const double *const *ltc;
+    int nlfc; const double *const *lfc;
+
+    int nnlic; ntg_nlicf_t nlicf;
+    int nnltc; ntg_nltcf_t nltcf;
+    int nnlfc; ntg_nlfcf_t nlfcf;
+
+    int ninitialconstrav;    const AV *initialconstrav;
+    int ntrajectoryconstrav; const AV *trajectoryconstrav;
+    int nfinalconstrav;      const AV *finalconstrav;
+
+    const double *lowerb; /* [nlic+nltc+nlfc+nnlic+nnltc+nnlfc], may be NULL */
+    const double *upperb;
+
+    int nicf; ntg_icf_t icf;
+    int nucf; ntg_ucf_t ucf;
+    int nfcf; ntg_fcf_t fcf;
+
+    int ninitialcostav;    const AV *initialcostav;
+    int ntrajectorycostav; const AV *trajectorycostav;
+    int nfinalcostav;      const AV *finalcostav;
+} ntgb_setup;
+
+typedef struct ntgb_problem ntgb_problem; /* opaque */
+
+/* sizes derived at create time (reference src/colloc.c:34-52, src/ntg.c:155-157) */
+typedef struct ntgb_dims {
+    int nout, nbps;
+    int nC;      /* number of coefficients = NPSOL n                     */
+    int nz;      /* sum_j maxderiv_j                                     */
+    int nZ;      /* nz * nbps                                            */
+    int nclin;   /* nlic + nltc*nbps + nlfc                              */
+    int ncnln;   /* nnlic + nnltc*nbps + nnlfc                           */
+    int sorder;  /* S = sum_j order_j = band width of one Jacobian row   */
+    int device;  /* CUDA device ordinal the tables live on               */
+} ntgb_dims;
+
+/* Jacobian layouts for ntgb_eval */
+#define NTGB_JAC_NONE  0
+/* NPSOL layout: per problem column-major ncnln x nC, ldJ = ncnln
+ * (reference src/ntg.c:217-220).  Only band entries are written; the caller
+ * zeroes the buffer once, exactly as the reference's one-time calloc does. */
+#define NTGB_JAC_DENSE 1
+/* Band-compact: per problem ncnln x S values.  Trajectory rows are stored
+ * breakpoint-fastest: value of (row = nnlic + m*nbps + bp, band slot s) is at
+ *   Jb[p*ncnln*S + nnlic*S + (m*S + s)*nbps + bp];
+ * initial rows r at Jb[p*ncnln*S + r*S + s]; final rows r at
+ *   Jb[p*ncnln*S + (nnlic + nnltc*nbps)*S + r*S + s].
+ * Band slot s = jk0[j] + k maps to column col0[row][j] + k (ntgb_pattern). */
+#define NTGB_JAC_BAND  2
+
+/*
+ * One batched evaluation.  All pointers are DEVICE pointers (or NULL to skip
+ * an output).  mode_obj / mode_con follow NPSOL: 0 values, 1 derivatives,
+ * 2 both, -1 skip that half entirely.
+ */
+typedef struct ntgb_eval_args {
+    int P;               /* number of problems in the batch                    */
+    const double *C;     /* [P][nC] coefficients, problem-major                */
+    int mode_obj;
+    int mode_con;
+    int nstate;          /* forwarded to callbacks (NPSOL: 1 on first call)    */
+    double *f;           /* [P]           objective (modes 0,2)                */
+    double *g;           /* [P][nC]       objective gradient (modes 1,2)       */
+    double *c;           /* [P][ncnln]    nonlinear constraints (modes 0,2)    */
+    double *J;           /* Jacobian, layout jac_layout (modes 1,2)            */
+    int jac_layout;
+    double *Z;           /* [P][nZ] flat outputs and derivatives, or NULL      */
+    double *result;      /* [P][2] = (objective, max nonlinear violation), or NULL */
+    void *stream;        /* cudaStream_t                                       */
+} ntgb_eval_args;
+
+/* error codes */
+#define NTGB_OK        0
+#define NTGB_EINVAL   -1  /* bad argument / shape contract violated            */
+#define NTGB_ENOPACK  -2  /* callbacks not found in any registered device pack */
+#define NTGB_ECUDA    -3  /* CUDA runtime failure (includes: no device)        */
+#define NTGB_ELIMIT   -4  /* problem exceeds the pack's compile-time bounds    */
+#define NTGB_ENOMEM   -5
+
+const char *ntgb_last_error(void);
+const char *ntgb_version(void);
+
+int  ntgb_create(ntgb_problem **out, const ntgb_setup *setup, int device);
+void ntgb_destroy(ntgb_problem *pb);
+int  ntgb_get_dims(const ntgb_problem *pb, ntgb_dims *dims);
+
+/* device buffers in, device buffers out, asynchronous on args->stream */
+int  ntgb_eval(ntgb_problem *pb, const ntgb_eval_args *args);
+/* same call with HOST buffers: H2D of C, launch, D2H of the requested outputs,
+ * synchronous.  This is what ntg()'s funobj/funcon trampolines use. */
+int  ntgb_eval_host(ntgb_problem *pb, const ntgb_eval_args *host_args);
+
+/*
+ * One-time tables built on the device by K0 (replaces CollocMatrix + PGS,
+ * reference src/colloc.c:57-117), copied back for inspection / parity:
+ *   B      [sum_j nbps*order_j*maxderiv_j]  per output contiguous,
+ *          index (bp*order_j + k)*maxderiv_j + d   (reference block layout)
+ *   offset [nout*nbps]    block[bp].offset            (src/colloc.c:108)
+ *   left   [nout*nbps]    interv() result on the augmented knots, 1-based
+ * Any pointer may be NULL.
+ */
+int  ntgb_get_tables(const ntgb_problem *pb, double *B, int *offset, int *left);
+/* augmented knot vector of output j (length n_j + order_j), host copy */
+int  ntgb_get_augknots(const ntgb_problem *pb, int j, double *t, int *len);
+
+/* Jacobian sparsity: col0[row*nout + j] = first column of output j's band in
+ * that row (reference src/colloc.c:243-316); jk0[j] = band slot of (j,k=0). */
+int  ntgb_get_pattern(const ntgb_problem *pb, int *col0, int *jk0);
+
+/* Linear constraints (reference src/constraints.c:198-261, src/ntg.c:162-206):
+ * A is nclin x nC column-major (ldA = nclin), host memory. */
+int  ntgb_get_linear(const ntgb_problem *pb, double *A);
+/* NPSOL bound vectors bl/bu of length nC+nclin+ncnln (src/constraints.c:5-33) */
+int  ntgb_get_bounds(const ntgb_problem *pb, double *bl, double *bu);
+/* batched A*C and linear violation on the device: lin [P][nclin], viol [P] */
+int  ntgb_eval_linear(ntgb_problem *pb, int P, const double *C, double *lin,
+                      double *viol, void *stream);
+
+/* Batched SplineInterp (reference src/colloc.c:449-484): for every problem p
+ * and time t[i], out[(p*nt + i)*nz + iz_j + d].  Device pointers. */
+int  ntgb_spline_interp(ntgb_problem *pb, int P, const double *C, int nt,
+                        const double *t, double *out, void *stream);
+
+/* ---- callback packs ------------------------------------------------------ */
+/*
+ * A pack is a shared object produced by tools/ntg_pack.py from a user's
+ * UNMODIFIED C file: the callbacks are compiled a second time as __device__
+ * code and the fused evaluator is instantiated on them.  Its static
+ * initialiser calls ntgb_register_pack().  Lookup is by the callbacks' host
+ * addresses, so an unchanged ntg(..., ucf, ...) call finds its kernel.
+ */
+struct ntgb_launch; /* internal, see ntg_b200/csrc/ntg_kernel_args.h */
+typedef struct ntgb_pack {
+    const char *name;
+    ntg_icf_t   icf;
+    ntg_ucf_t   ucf;
+    ntg_fcf_t   fcf;
+    ntg_nlicf_t nlicf;
+    ntg_nltcf_t nltcf;
+    ntg_nlfcf_t nlfcf;
+    int max_nout, max_maxderiv, max_order; /* compile-time bounds of the kernel */
+    int max_nnlic, max_nnltc, max_nnlfc;
+    int exact;  /* 1: reference operation order, no FMA contraction */
+    int (*launch)(const struct ntgb_launch *);
+} ntgb_pack;
+
+int ntgb_register_pack(const ntgb_pack *pack);
+const ntgb_pack *ntgb_find_pack(const char *name);
+int ntgb_num_packs(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NTG_B200_H_ */

@@ -1,0 +1,6 @@
+/* cost.h -- compatibility shim: the reference splits its public surface over
+ * several headers (reference src/cost.h); here everything lives in ntg.h. */
+#ifndef NTG_DROPIN_COST_SHIM_H_
+#define NTG_DROPIN_COST_SHIM_H_
+#include "ntg.h"
+#endif

@@ -1,0 +1,6 @@
+/* matrix.h -- compatibility shim: the reference splits its public surface over
+ * several headers (reference src/matrix.h); here everything lives in ntg.h. */
+#ifndef NTG_DROPIN_MATRIX_SHIM_H_
+#define NTG_DROPIN_MATRIX_SHIM_H_
+#include "ntg.h"
+#endif

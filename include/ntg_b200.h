@@ -199,8 +199,12 @@ typedef struct ntgb_pack {
     ntg_nlicf_t nlicf;
     ntg_nltcf_t nltcf;
     ntg_nlfcf_t nlfcf;
-    int max_nout, max_maxderiv, max_order; /* compile-time bounds of the kernel */
+    /* compile-time shape of the kernel: nout and maxderiv[] are EXACT (the
+     * callbacks hard-code zp[j][d] and the df index layout), order is a bound,
+     * constraint counts are exact when the kind is enabled */
+    int max_nout, max_maxderiv, max_order;
     int max_nnlic, max_nnltc, max_nnlfc;
+    int maxderiv[8];
     int exact;  /* 1: reference operation order, no FMA contraction */
     int (*launch)(const struct ntgb_launch *);
 } ntgb_pack;

@@ -83,6 +83,7 @@ class NtgbPack(C.Structure):
         ("nlicf", C.c_void_p), ("nltcf", C.c_void_p), ("nlfcf", C.c_void_p),
         ("max_nout", C.c_int), ("max_maxderiv", C.c_int), ("max_order", C.c_int),
         ("max_nnlic", C.c_int), ("max_nnltc", C.c_int), ("max_nnlfc", C.c_int),
+        ("maxderiv", C.c_int * 8),
         ("exact", C.c_int),
         ("launch", C.c_void_p),
     ]

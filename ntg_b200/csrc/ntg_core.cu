@@ -1,0 +1,749 @@
+/*
+ * ntg_core.cu -- core of libntg_b200.so: the C ABI of include/ntg_b200.h.
+ *
+ *   - pack registry (callback host address -> instantiated device evaluator)
+ *   - K0: one-time device build of the collocation tables (replaces
+ *     ConcatCollocMatrix / CollocMatrix + PGS, reference src/colloc.c:15-117)
+ *   - problem handles, batched evaluation entry points (device and host
+ *     buffers), table / pattern / bounds getters
+ *   - "next" rows of SURVEY.md section 8(f): linear-constraint matrix and batched
+ *     A*C (src/constraints.c:198-261), bound expansion (src/constraints.c:5-33),
+ *     batched SplineInterp (src/colloc.c:449-484)
+ *
+ * Built with -fmad=false: every table and linear-constraint entry is plain
+ * IEEE double evaluated in the reference's order.
+ * There is no CPU evaluation path in this library.
+ */
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "ntg_b200.h"
+#include "ntg_kernel_args.h"
+#include "pgs_device.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t e_ = (expr);                                                             \
+        if (e_ != cudaSuccess)                                                               \
+            return fail(NTGB_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                 \
+    } while (0)
+
+std::mutex g_reg_mu;
+std::vector<ntgb_pack> &registry()
+{
+    static std::vector<ntgb_pack> r;
+    return r;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+} /* namespace */
+
+struct ntgb_problem {
+    int device = 0;
+    ntgb_dims dims{};
+    ntgb_devtab tab{};
+    const ntgb_pack *pack = nullptr;
+    ntgb_pack pack_copy{};
+    int sm_count = 0, max_smem_optin = 0;
+    /* host copies of the setup */
+    std::vector<int> order, mult, maxderiv, ninterv, ncoef;
+    std::vector<std::vector<double>> knots, augknots;
+    std::vector<double> bps;
+    int nlic = 0, nltc = 0, nlfc = 0, nnlic = 0, nnltc = 0, nnlfc = 0;
+    std::vector<double> lic, ltc, lfc; /* row-major [n][nz] */
+    std::vector<double> lowerb, upperb;
+    /* host copies of K0 output */
+    std::vector<double> hB;            /* reference block layout, outputs concatenated */
+    std::vector<size_t> hB_off;        /* start of output j in hB */
+    std::vector<int> hoff, hleft;      /* [nout][nbps] */
+    std::vector<int> col0;             /* [ncnln][nout] */
+    std::vector<double> A;             /* nclin x nC column-major */
+    /* device-side linear constraints in band form */
+    double *dAband = nullptr;          /* [nclin][S] */
+    int *dAcol0 = nullptr;             /* [nclin][nout] */
+    double *dlin_lb = nullptr, *dlin_ub = nullptr; /* [nclin] expanded */
+    /* spline-interp device description */
+    double *daug[NTGB_MAXOUT] = {nullptr};
+    double *dknots[NTGB_MAXOUT] = {nullptr};
+    std::vector<void *> allocs;
+    /* scratch for ntgb_eval_host */
+    struct {
+        int P = 0, jac_layout = -1;
+        double *C = nullptr, *f = nullptr, *g = nullptr, *c = nullptr, *J = nullptr, *Z = nullptr,
+               *result = nullptr;
+        size_t Jbytes = 0;
+    } hs;
+    cudaStream_t hstream = nullptr;
+};
+
+namespace {
+
+template <class T>
+int dev_alloc(ntgb_problem *pb, T **ptr, size_t n)
+{
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (n > 0 ? n : 1) * sizeof(T));
+    if (e != cudaSuccess) return fail(NTGB_ENOMEM, "cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e));
+    pb->allocs.push_back(p);
+    *ptr = static_cast<T *>(p);
+    return 0;
+}
+
+template <class T>
+int dev_upload(ntgb_problem *pb, T **ptr, const T *src, size_t n)
+{
+    int rc = dev_alloc(pb, ptr, n);
+    if (rc) return rc;
+    if (n) CUDA_TRY(cudaMemcpy(*ptr, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+/* ------------------------------- K0 kernels ------------------------------- */
+
+/* augmented knots (PGS `knots`, reference src/colloc.c:92-93) */
+__global__ void k0_augknots(const double *brk, int ninterv, int order, int mult, double *aug, int naug)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < naug) aug[i] = ntgb::pgs_augknot(brk, ninterv, order, mult, i);
+}
+
+/* one thread per breakpoint: interv + bsplvd on the augmented knots, interv on
+ * the raw knots for the block offset (reference src/colloc.c:95-111) */
+__global__ void k0_tables(const double *aug, int naug, const double *brk, int nknots, const double *bps,
+                          int nbps, int order, int mult, int md, double *Bn, double *Bt, int *off,
+                          int *left_out)
+{
+    const int bp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bp >= nbps) return;
+    double a[PGS_MAXK * PGS_MAXK];
+    double db[PGS_MAXK * PGS_MAXK];
+    const double x = bps[bp];
+    const int left = ntgb::pgs_interv(aug, naug, x);
+    for (int i = 0; i < order * md; i++) db[i] = 0.0;
+    ntgb::pgs_bsplvd(aug, order, x, left, a, db, md);
+    for (int k = 0; k < order; k++)
+        for (int d = 0; d < md; d++) {
+            const double v = db[d * order + k];
+            Bn[((size_t)bp * order + k) * md + d] = v;
+            Bt[((size_t)k * md + d) * nbps + bp] = v;
+        }
+    const int lk = ntgb::pgs_interv(brk, nknots, x);
+    off[bp] = (lk - 1) * (order - mult);
+    left_out[bp] = left;
+}
+
+/* batched linear constraints: lin[p][r] = sum over the band of A[r][.]*C[p][.]
+ * (what NPSOL computes as A*x for its linear rows) and the linear violation */
+__global__ void k_linear(const double *Aband, const int *Acol0, const double *lb, const double *ub,
+                         int nclin, int nout, int S, ntgb_devtab T, int P, const double *C,
+                         double *lin, double *viol)
+{
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (long long)P * nclin) return;
+    const int p = (int)(q / nclin), r = (int)(q - (long long)p * nclin);
+    const double *Cp = C + (size_t)p * T.nC;
+    double acc = 0.0;
+    for (int j = 0; j < nout; j++) {
+        const int c0 = Acol0[r * nout + j];
+        for (int k = 0; k < T.order[j]; k++) acc = acc + Aband[(size_t)r * S + T.jk0[j] + k] * Cp[c0 + k];
+    }
+    if (lin) lin[(size_t)p * nclin + r] = acc;
+    if (viol) {
+        double v = 0.0;
+        if (lb[r] - acc > v) v = lb[r] - acc;
+        if (acc - ub[r] > v) v = acc - ub[r];
+        if (v > 0.0) atomicMax(reinterpret_cast<unsigned long long *>(viol + p),
+                               (unsigned long long)__double_as_longlong(v));
+    }
+}
+
+/* batched SplineInterp, reference src/colloc.c:449-484: one thread per
+ * (problem, time, output); interv + bsplvd at an arbitrary x on the device */
+struct InterpDesc {
+    int nout, nC, nz;
+    int order[NTGB_MAXOUT], mult[NTGB_MAXOUT], md[NTGB_MAXOUT], ninterv[NTGB_MAXOUT], ncoef[NTGB_MAXOUT];
+    int iC[NTGB_MAXOUT], iz[NTGB_MAXOUT];
+    const double *aug[NTGB_MAXOUT];
+    const double *knots[NTGB_MAXOUT];
+};
+
+__global__ void k_spline_interp(InterpDesc D, int P, const double *C, int nt, const double *t, double *out)
+{
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)P * nt * D.nout;
+    if (q >= total) return;
+    const int j = (int)(q % D.nout);
+    const long long pi = q / D.nout;
+    const int i = (int)(pi % nt);
+    const int p = (int)(pi / nt);
+    const int order = D.order[j], md = D.md[j];
+    double a[PGS_MAXK * PGS_MAXK];
+    double db[PGS_MAXK * PGS_MAXK];
+    const double x = t[i];
+    const int naug = D.ncoef[j] + order;
+    const int left1 = ntgb::pgs_interv(D.aug[j], naug, x);
+    for (int e = 0; e < order * md; e++) db[e] = 0.0;
+    ntgb::pgs_bsplvd(D.aug[j], order, x, left1, a, db, md);
+    const int left2 = ntgb::pgs_interv(D.knots[j], D.ninterv[j] + 1, x);
+    const int offset = (left2 - 1) * (order - D.mult[j]);
+    const double *coefs = C + (size_t)p * D.nC + D.iC[j];
+    for (int d = 0; d < md; d++) {
+        double f = 0.0;
+        for (int k = 0; k < order; k++) f = f + db[d * order + k] * coefs[offset + k];
+        out[((size_t)p * nt + i) * D.nz + D.iz[j] + d] = f;
+    }
+}
+
+int check_avs(const AV *av, int n, const ntgb_setup *s, const char *what)
+{
+    if (n < 0 || (n > 0 && av == nullptr)) return fail(NTGB_EINVAL, "%s: bad active-variable list", what);
+    for (int i = 0; i < n; i++)
+        if (av[i].output < 0 || av[i].output >= s->nout || av[i].deriv < 0 ||
+            av[i].deriv >= s->maxderiv[av[i].output])
+            return fail(NTGB_EINVAL, "%s[%d] = {%d,%d} out of range", what, i, av[i].output, av[i].deriv);
+    return 0;
+}
+
+void add_mask(unsigned (*mask)[NTGB_MAXOUT], const AV *av, int n, int cls_bits)
+{
+    for (int cls = 0; cls < 4; cls++) {
+        const bool first = cls & 1, last = cls & 2;
+        const bool hit = (cls_bits == 0) || (cls_bits == 1 && first) || (cls_bits == 2 && last);
+        if (!hit) continue;
+        for (int i = 0; i < n; i++) mask[cls][av[i].output] |= 1u << av[i].deriv;
+    }
+}
+
+const ntgb_pack *match_pack(const ntgb_setup *s)
+{
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    for (const ntgb_pack &pk : registry()) {
+        bool ok = true, any = false;
+        auto chk = [&](int count, const void *want, const void *have) {
+            if (count != 0 && want != nullptr) {
+                any = true;
+                if (want != have) ok = false;
+            }
+        };
+        chk(s->nicf, (const void *)s->icf, (const void *)pk.icf);
+        chk(s->nucf, (const void *)s->ucf, (const void *)pk.ucf);
+        chk(s->nfcf, (const void *)s->fcf, (const void *)pk.fcf);
+        chk(s->nnlic, (const void *)s->nlicf, (const void *)pk.nlicf);
+        chk(s->nnltc, (const void *)s->nltcf, (const void *)pk.nltcf);
+        chk(s->nnlfc, (const void *)s->nlfcf, (const void *)pk.nlfcf);
+        if (ok && any) return &pk;
+    }
+    return nullptr;
+}
+
+/* one Jacobian-style band row on the host from a constant derivative vector
+ * (linear constraints: InitialConstraintsMatrix etc., src/constraints.c:225-261) */
+void host_band_row(const ntgb_problem *pb, const double *dz, int bp, double *band)
+{
+    for (int j = 0; j < pb->dims.nout; j++) {
+        const int order = pb->order[j], md = pb->maxderiv[j];
+        const double *B = pb->hB.data() + pb->hB_off[j] + (size_t)bp * order * md;
+        for (int k = 0; k < order; k++) {
+            double acc = 0.0;
+            for (int l = 0; l < md; l++) acc = acc + dz[pb->tab.iz[j] + l] * B[k * md + l];
+            band[pb->tab.jk0[j] + k] = acc;
+        }
+    }
+}
+
+} /* namespace */
+
+extern "C" {
+
+const char *ntgb_last_error(void) { return g_err.c_str(); }
+const char *ntgb_version(void) { return "ntg_b200 0.1 (sm_100a, kernel ABI 3)"; }
+
+int ntgb_register_pack(const ntgb_pack *pack)
+{
+    if (!pack || !pack->launch || !pack->name) return fail(NTGB_EINVAL, "ntgb_register_pack: null pack");
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    for (ntgb_pack &pk : registry())
+        if (strcmp(pk.name, pack->name) == 0) {
+            pk = *pack;
+            return 0;
+        }
+    registry().push_back(*pack);
+    return 0;
+}
+
+const ntgb_pack *ntgb_find_pack(const char *name)
+{
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    for (const ntgb_pack &pk : registry())
+        if (strcmp(pk.name, name) == 0) return &pk;
+    return nullptr;
+}
+
+int ntgb_num_packs(void)
+{
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    return (int)registry().size();
+}
+
+void ntgb_destroy(ntgb_problem *pb)
+{
+    if (!pb) return;
+    DeviceGuard dg(pb->device);
+    for (void *p : pb->allocs) cudaFree(p);
+    double *hsp[] = {pb->hs.C, pb->hs.f, pb->hs.g, pb->hs.c, pb->hs.J, pb->hs.Z, pb->hs.result};
+    for (double *p : hsp)
+        if (p) cudaFree(p);
+    if (pb->hstream) cudaStreamDestroy(pb->hstream);
+    delete pb;
+}
+
+int ntgb_create(ntgb_problem **out, const ntgb_setup *s, int device)
+{
+    if (!out || !s) return fail(NTGB_EINVAL, "ntgb_create: null argument");
+    *out = nullptr;
+    if (s->nout < 1 || s->nout > NTGB_MAXOUT)
+        return fail(NTGB_EINVAL, "nout = %d outside [1,%d]", s->nout, NTGB_MAXOUT);
+    if (s->nbps < 2 || !s->bps) return fail(NTGB_EINVAL, "need at least 2 breakpoints");
+    if (!s->kninterv || !s->knots || !s->order || !s->mult || !s->maxderiv)
+        return fail(NTGB_EINVAL, "ntgb_create: null spline description");
+    for (int j = 0; j < s->nout; j++) {
+        /* maxderiv <= order <= 20: PGS bsplvd/bsplvb limits */
+        if (s->order[j] < 1 || s->order[j] > NTGB_MAXORDER)
+            return fail(NTGB_EINVAL, "order[%d] = %d outside [1,%d]", j, s->order[j], NTGB_MAXORDER);
+        if (s->maxderiv[j] < 1 || s->maxderiv[j] > s->order[j])
+            return fail(NTGB_EINVAL, "maxderiv[%d] = %d outside [1,order]", j, s->maxderiv[j]);
+        if (s->mult[j] < 0 || s->mult[j] >= s->order[j])
+            return fail(NTGB_EINVAL, "mult[%d] = %d outside [0,order)", j, s->mult[j]);
+        if (s->kninterv[j] < 1 || !s->knots[j]) return fail(NTGB_EINVAL, "output %d: bad knots", j);
+    }
+    int rc;
+    if ((rc = check_avs(s->initialcostav, s->ninitialcostav, s, "initialcostav"))) return rc;
+    if ((rc = check_avs(s->trajectorycostav, s->ntrajectorycostav, s, "trajectorycostav"))) return rc;
+    if ((rc = check_avs(s->finalcostav, s->nfinalcostav, s, "finalcostav"))) return rc;
+    if ((rc = check_avs(s->initialconstrav, s->ninitialconstrav, s, "initialconstrav"))) return rc;
+    if ((rc = check_avs(s->trajectoryconstrav, s->ntrajectoryconstrav, s, "trajectoryconstrav"))) return rc;
+    if ((rc = check_avs(s->finalconstrav, s->nfinalconstrav, s, "finalconstrav"))) return rc;
+
+    const ntgb_pack *pk = match_pack(s);
+    if (!pk)
+        return fail(NTGB_ENOPACK,
+                    "no registered device pack provides these callbacks (%d packs loaded): compile the "
+                    "callback file with tools/ntg_pack.py and load the resulting shared object",
+                    ntgb_num_packs());
+    if (pk->max_nout != s->nout)
+        return fail(NTGB_ELIMIT, "pack '%s' is compiled for nout = %d, problem has %d", pk->name, pk->max_nout, s->nout);
+    for (int j = 0; j < s->nout; j++) {
+        if (pk->maxderiv[j] != s->maxderiv[j])
+            return fail(NTGB_ELIMIT, "pack '%s' is compiled for maxderiv[%d] = %d, problem has %d", pk->name, j,
+                        pk->maxderiv[j], s->maxderiv[j]);
+        if (s->order[j] > pk->max_order)
+            return fail(NTGB_ELIMIT, "pack '%s' is compiled for order <= %d, output %d has %d", pk->name,
+                        pk->max_order, j, s->order[j]);
+    }
+    if ((s->nnlic && s->nnlic != pk->max_nnlic) || (s->nnltc && s->nnltc != pk->max_nnltc) ||
+        (s->nnlfc && s->nnlfc != pk->max_nnlfc))
+        return fail(NTGB_ELIMIT, "pack '%s' is compiled for (nnlic,nnltc,nnlfc) = (%d,%d,%d), problem has (%d,%d,%d)",
+                    pk->name, pk->max_nnlic, pk->max_nnltc, pk->max_nnlfc, s->nnlic, s->nnltc, s->nnlfc);
+
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(NTGB_ECUDA, "no CUDA device available (%s); this library has no CPU path",
+                    ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
+    if (device < 0 || device >= ndev) return fail(NTGB_EINVAL, "device %d not in [0,%d)", device, ndev);
+    DeviceGuard dg(device);
+    if (!dg.ok) return fail(NTGB_ECUDA, "cannot select device %d", device);
+
+    ntgb_problem *pb = new ntgb_problem();
+    pb->device = device;
+    pb->pack_copy = *pk;
+    pb->pack = &pb->pack_copy;
+    struct Cleanup {
+        ntgb_problem *p;
+        ~Cleanup() { if (p) ntgb_destroy(p); }
+    } cleanup{pb};
+
+    CUDA_TRY(cudaDeviceGetAttribute(&pb->sm_count, cudaDevAttrMultiProcessorCount, device));
+    CUDA_TRY(cudaDeviceGetAttribute(&pb->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+
+    ntgb_devtab &T = pb->tab;
+    const int nout = s->nout, nbps = s->nbps;
+    T.nout = nout; T.nbps = nbps;
+    T.nicf = s->nicf; T.nucf = s->nucf; T.nfcf = s->nfcf;
+    T.nnlic = s->nnlic; T.nnltc = s->nnltc; T.nnlfc = s->nnlfc;
+    pb->nlic = s->nlic; pb->nltc = s->nltc; pb->nlfc = s->nlfc;
+    pb->nnlic = s->nnlic; pb->nnltc = s->nnltc; pb->nnlfc = s->nnlfc;
+    pb->bps.assign(s->bps, s->bps + nbps);
+    pb->hB_off.resize(nout);
+    size_t btot = 0;
+    for (int j = 0; j < nout; j++) {
+        const int order = s->order[j], mult = s->mult[j], md = s->maxderiv[j], ni = s->kninterv[j];
+        const int n = ni * (order - mult) + mult; /* reference src/colloc.c:67 */
+        pb->order.push_back(order); pb->mult.push_back(mult); pb->maxderiv.push_back(md);
+        pb->ninterv.push_back(ni); pb->ncoef.push_back(n);
+        pb->knots.emplace_back(s->knots[j], s->knots[j] + ni + 1);
+        T.order[j] = order; T.mult[j] = mult; T.maxderiv[j] = md; T.ncoef[j] = n;
+        T.iC[j] = T.nC; T.iz[j] = T.nz; T.jk0[j] = T.S;
+        T.nC += n; T.nz += md; T.S += order;
+        pb->hB_off[j] = btot;
+        btot += (size_t)nbps * order * md;
+    }
+    for (int j = 0; j < nout; j++) T.iZ[j] = T.iz[j] * nbps; /* reference src/colloc.c:43 */
+    T.nZ = T.nz * nbps;
+    T.ncnln = s->nnlic + s->nnltc * nbps + s->nnlfc;
+    pb->dims.nout = nout; pb->dims.nbps = nbps; pb->dims.nC = T.nC; pb->dims.nz = T.nz; pb->dims.nZ = T.nZ;
+    pb->dims.nclin = s->nlic + s->nltc * nbps + s->nlfc;
+    pb->dims.ncnln = T.ncnln; pb->dims.sorder = T.S; pb->dims.device = device;
+
+    /* active-variable masks: updateZ is only called for kinds whose count != 0
+     * (reference src/ntg.c:287-292, :348-353) */
+    if (s->nicf != 0) add_mask(T.avmask, s->initialcostav, s->ninitialcostav, 1);
+    if (s->nucf != 0) add_mask(T.avmask, s->trajectorycostav, s->ntrajectorycostav, 0);
+    if (s->nfcf != 0) add_mask(T.avmask, s->finalcostav, s->nfinalcostav, 2);
+    if (s->nnlic != 0) add_mask(T.avmask, s->initialconstrav, s->ninitialconstrav, 1);
+    if (s->nnltc != 0) add_mask(T.avmask, s->trajectoryconstrav, s->ntrajectoryconstrav, 0);
+    if (s->nnlfc != 0) add_mask(T.avmask, s->finalconstrav, s->nfinalconstrav, 2);
+
+    /* ---- K0: tables on the device ---- */
+    double *dbps = nullptr;
+    if ((rc = dev_upload(pb, &dbps, pb->bps.data(), (size_t)nbps))) return rc;
+    T.bps = dbps;
+    pb->hB.resize(btot);
+    pb->hoff.resize((size_t)nout * nbps);
+    pb->hleft.resize((size_t)nout * nbps);
+    pb->augknots.resize(nout);
+    for (int j = 0; j < nout; j++) {
+        const int order = T.order[j], mult = T.mult[j], md = T.maxderiv[j], ni = pb->ninterv[j];
+        const int naug = T.ncoef[j] + order;
+        double *dk = nullptr, *daug = nullptr, *dBn = nullptr, *dBt = nullptr;
+        int *doff = nullptr, *dleft = nullptr;
+        if ((rc = dev_upload(pb, &dk, pb->knots[j].data(), (size_t)ni + 1))) return rc;
+        if ((rc = dev_alloc(pb, &daug, (size_t)naug))) return rc;
+        if ((rc = dev_alloc(pb, &dBn, (size_t)nbps * order * md))) return rc;
+        if ((rc = dev_alloc(pb, &dBt, (size_t)nbps * order * md))) return rc;
+        if ((rc = dev_alloc(pb, &doff, (size_t)nbps))) return rc;
+        if ((rc = dev_alloc(pb, &dleft, (size_t)nbps))) return rc;
+        k0_augknots<<<(naug + 127) / 128, 128>>>(dk, ni, order, mult, daug, naug);
+        k0_tables<<<(nbps + 63) / 64, 64>>>(daug, naug, dk, ni + 1, dbps, nbps, order, mult, md, dBn, dBt, doff, dleft);
+        CUDA_TRY(cudaGetLastError());
+        T.Bn[j] = dBn; T.Bt[j] = dBt; T.off[j] = doff;
+        pb->daug[j] = daug; pb->dknots[j] = dk;
+        pb->augknots[j].resize(naug);
+        CUDA_TRY(cudaMemcpy(pb->augknots[j].data(), daug, sizeof(double) * naug, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(pb->hB.data() + pb->hB_off[j], dBn, sizeof(double) * (size_t)nbps * order * md,
+                            cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(pb->hoff.data() + (size_t)j * nbps, doff, sizeof(int) * nbps, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(pb->hleft.data() + (size_t)j * nbps, dleft, sizeof(int) * nbps, cudaMemcpyDeviceToHost));
+        for (int bp = 0; bp < nbps; bp++) {
+            const int o = pb->hoff[(size_t)j * nbps + bp];
+            if (o < 0 || o + order > T.ncoef[j])
+                return fail(NTGB_EINVAL, "output %d breakpoint %d: coefficient window [%d,%d) outside [0,%d)", j, bp, o,
+                            o + order, T.ncoef[j]);
+        }
+    }
+
+    /* column support for the gradient gather: first/last breakpoint whose band holds column c */
+    {
+        std::vector<int> lo(T.nC, nbps), hi(T.nC, -1);
+        for (int j = 0; j < nout; j++)
+            for (int bp = 0; bp < nbps; bp++) {
+                const int o = pb->hoff[(size_t)j * nbps + bp];
+                for (int k = 0; k < T.order[j]; k++) {
+                    const int c = T.iC[j] + o + k;
+                    if (bp < lo[c]) lo[c] = bp;
+                    if (bp > hi[c]) hi[c] = bp;
+                }
+            }
+        int *dlo = nullptr, *dhi = nullptr;
+        if ((rc = dev_upload(pb, &dlo, lo.data(), (size_t)T.nC))) return rc;
+        if ((rc = dev_upload(pb, &dhi, hi.data(), (size_t)T.nC))) return rc;
+        T.col_lo = dlo; T.col_hi = dhi;
+    }
+
+    /* Jacobian row pattern (reference src/colloc.c:243-316) */
+    pb->col0.resize((size_t)(T.ncnln > 0 ? T.ncnln : 1) * nout);
+    {
+        int row = 0;
+        for (int r = 0; r < s->nnlic; r++, row++)
+            for (int j = 0; j < nout; j++) pb->col0[(size_t)row * nout + j] = T.iC[j];
+        for (int m = 0; m < s->nnltc; m++)
+            for (int bp = 0; bp < nbps; bp++, row++)
+                for (int j = 0; j < nout; j++)
+                    pb->col0[(size_t)row * nout + j] = T.iC[j] + pb->hoff[(size_t)j * nbps + bp];
+        for (int r = 0; r < s->nnlfc; r++, row++)
+            for (int j = 0; j < nout; j++)
+                pb->col0[(size_t)row * nout + j] = T.iC[j] + pb->hoff[(size_t)j * nbps + nbps - 1];
+    }
+
+    /* bounds (compact), nonlinear part on the device for the violation epilogue */
+    const int nlin_b = s->nlic + s->nltc + s->nlfc, nnl_b = s->nnlic + s->nnltc + s->nnlfc;
+    pb->lowerb.assign((size_t)nlin_b + nnl_b, -DBL_MAX);
+    pb->upperb.assign((size_t)nlin_b + nnl_b, DBL_MAX);
+    if (s->lowerb) pb->lowerb.assign(s->lowerb, s->lowerb + nlin_b + nnl_b);
+    if (s->upperb) pb->upperb.assign(s->upperb, s->upperb + nlin_b + nnl_b);
+    {
+        double *dlb = nullptr, *dub = nullptr;
+        if ((rc = dev_upload(pb, &dlb, pb->lowerb.data() + nlin_b, (size_t)nnl_b))) return rc;
+        if ((rc = dev_upload(pb, &dub, pb->upperb.data() + nlin_b, (size_t)nnl_b))) return rc;
+        T.nl_lb = dlb; T.nl_ub = dub;
+    }
+
+    /* linear constraints: A (NPSOL layout, host) and band form (device) */
+    auto copy_rows = [&](std::vector<double> &dst, const double *const *src, int n) {
+        dst.assign((size_t)n * T.nz, 0.0);
+        for (int r = 0; r < n; r++)
+            for (int q = 0; q < T.nz; q++) dst[(size_t)r * T.nz + q] = src[r][q];
+    };
+    if (s->nlic) { if (!s->lic) return fail(NTGB_EINVAL, "nlic > 0 but lic == NULL"); copy_rows(pb->lic, s->lic, s->nlic); }
+    if (s->nltc) { if (!s->ltc) return fail(NTGB_EINVAL, "nltc > 0 but ltc == NULL"); copy_rows(pb->ltc, s->ltc, s->nltc); }
+    if (s->nlfc) { if (!s->lfc) return fail(NTGB_EINVAL, "nlfc > 0 but lfc == NULL"); copy_rows(pb->lfc, s->lfc, s->nlfc); }
+    const int nclin = pb->dims.nclin;
+    if (nclin > 0) {
+        std::vector<double> band((size_t)nclin * T.S, 0.0), llb(nclin), lub(nclin);
+        std::vector<int> acol0((size_t)nclin * nout);
+        pb->A.assign((size_t)nclin * T.nC, 0.0);
+        int row = 0, bsrc = 0;
+        auto put = [&](const double *dz, int bp, bool initial, double lbv, double ubv) {
+            double *b = band.data() + (size_t)row * T.S;
+            host_band_row(pb, dz, bp, b);
+            for (int j = 0; j < nout; j++) {
+                const int c0 = T.iC[j] + (initial ? 0 : pb->hoff[(size_t)j * nbps + bp]);
+                acol0[(size_t)row * nout + j] = c0;
+                for (int k = 0; k < T.order[j]; k++) pb->A[(size_t)(c0 + k) * nclin + row] = b[T.jk0[j] + k];
+            }
+            llb[row] = lbv; lub[row] = ubv;
+            row++;
+        };
+        for (int r = 0; r < s->nlic; r++, bsrc++) put(&pb->lic[(size_t)r * T.nz], 0, true, pb->lowerb[bsrc], pb->upperb[bsrc]);
+        for (int r = 0; r < s->nltc; r++, bsrc++)
+            for (int bp = 0; bp < nbps; bp++) put(&pb->ltc[(size_t)r * T.nz], bp, false, pb->lowerb[bsrc], pb->upperb[bsrc]);
+        for (int r = 0; r < s->nlfc; r++, bsrc++) put(&pb->lfc[(size_t)r * T.nz], nbps - 1, false, pb->lowerb[bsrc], pb->upperb[bsrc]);
+        if ((rc = dev_upload(pb, &pb->dAband, band.data(), band.size()))) return rc;
+        if ((rc = dev_upload(pb, &pb->dAcol0, acol0.data(), acol0.size()))) return rc;
+        if ((rc = dev_upload(pb, &pb->dlin_lb, llb.data(), llb.size()))) return rc;
+        if ((rc = dev_upload(pb, &pb->dlin_ub, lub.data(), lub.size()))) return rc;
+    }
+    CUDA_TRY(cudaDeviceSynchronize());
+    cleanup.p = nullptr;
+    *out = pb;
+    return 0;
+}
+
+int ntgb_get_dims(const ntgb_problem *pb, ntgb_dims *dims)
+{
+    if (!pb || !dims) return fail(NTGB_EINVAL, "ntgb_get_dims: null argument");
+    *dims = pb->dims;
+    return 0;
+}
+
+int ntgb_get_tables(const ntgb_problem *pb, double *B, int *offset, int *left)
+{
+    if (!pb) return fail(NTGB_EINVAL, "null problem");
+    if (B) memcpy(B, pb->hB.data(), pb->hB.size() * sizeof(double));
+    if (offset) memcpy(offset, pb->hoff.data(), pb->hoff.size() * sizeof(int));
+    if (left) memcpy(left, pb->hleft.data(), pb->hleft.size() * sizeof(int));
+    return 0;
+}
+
+int ntgb_get_augknots(const ntgb_problem *pb, int j, double *t, int *len)
+{
+    if (!pb || j < 0 || j >= pb->dims.nout) return fail(NTGB_EINVAL, "bad output index");
+    if (len) *len = (int)pb->augknots[j].size();
+    if (t) memcpy(t, pb->augknots[j].data(), pb->augknots[j].size() * sizeof(double));
+    return 0;
+}
+
+int ntgb_get_pattern(const ntgb_problem *pb, int *col0, int *jk0)
+{
+    if (!pb) return fail(NTGB_EINVAL, "null problem");
+    if (col0 && pb->dims.ncnln > 0) memcpy(col0, pb->col0.data(), sizeof(int) * (size_t)pb->dims.ncnln * pb->dims.nout);
+    if (jk0) memcpy(jk0, pb->tab.jk0, sizeof(int) * pb->dims.nout);
+    return 0;
+}
+
+int ntgb_get_linear(const ntgb_problem *pb, double *A)
+{
+    if (!pb || !A) return fail(NTGB_EINVAL, "null argument");
+    if (pb->dims.nclin > 0) memcpy(A, pb->A.data(), pb->A.size() * sizeof(double));
+    return 0;
+}
+
+/* bounds(), reference src/constraints.c:5-33 with bigbnd = +-DBL_MAX (src/ntg.c:226-229) */
+int ntgb_get_bounds(const ntgb_problem *pb, double *bl, double *bu)
+{
+    if (!pb) return fail(NTGB_EINVAL, "null problem");
+    const int nbps = pb->dims.nbps;
+    for (int pass = 0; pass < 2; pass++) {
+        double *dst = pass ? bu : bl;
+        const std::vector<double> &b = pass ? pb->upperb : pb->lowerb;
+        if (!dst) continue;
+        size_t pos = 0, src = 0;
+        for (int i = 0; i < pb->dims.nC; i++) dst[pos++] = pass ? DBL_MAX : -DBL_MAX;
+        for (int i = 0; i < pb->nlic; i++) dst[pos++] = b[src++];
+        for (int i = 0; i < pb->nltc; i++, src++) for (int j = 0; j < nbps; j++) dst[pos++] = b[src];
+        for (int i = 0; i < pb->nlfc; i++) dst[pos++] = b[src++];
+        for (int i = 0; i < pb->nnlic; i++) dst[pos++] = b[src++];
+        for (int i = 0; i < pb->nnltc; i++, src++) for (int j = 0; j < nbps; j++) dst[pos++] = b[src];
+        for (int i = 0; i < pb->nnlfc; i++) dst[pos++] = b[src++];
+    }
+    return 0;
+}
+
+int ntgb_eval(ntgb_problem *pb, const ntgb_eval_args *a)
+{
+    if (!pb || !a) return fail(NTGB_EINVAL, "ntgb_eval: null argument");
+    if (a->P < 0) return fail(NTGB_EINVAL, "P = %d", a->P);
+    if (a->P == 0) return 0;
+    if (!a->C) return fail(NTGB_EINVAL, "ntgb_eval: C == NULL");
+    if (a->mode_obj < -1 || a->mode_obj > 2 || a->mode_con < -1 || a->mode_con > 2)
+        return fail(NTGB_EINVAL, "mode must be -1, 0, 1 or 2");
+    if (a->jac_layout < NTGB_JAC_NONE || a->jac_layout > NTGB_JAC_BAND)
+        return fail(NTGB_EINVAL, "unknown jac_layout %d", a->jac_layout);
+    DeviceGuard dg(pb->device);
+    if (!dg.ok) return fail(NTGB_ECUDA, "cannot select device %d", pb->device);
+    ntgb_launch L;
+    L.abi = NTGB_KERNEL_ABI;
+    L.tab = pb->tab;
+    L.args = *a;
+    L.sm_count = pb->sm_count;
+    L.max_smem_optin = pb->max_smem_optin;
+    const int rc = pb->pack->launch(&L);
+    if (rc == -1000) return fail(NTGB_ELIMIT, "problem needs more shared memory than the device offers");
+    if (rc != 0) return fail(NTGB_ECUDA, "kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+    return 0;
+}
+
+int ntgb_eval_host(ntgb_problem *pb, const ntgb_eval_args *h)
+{
+    if (!pb || !h) return fail(NTGB_EINVAL, "ntgb_eval_host: null argument");
+    if (h->P <= 0) return h->P == 0 ? 0 : fail(NTGB_EINVAL, "P = %d", h->P);
+    if (!h->C) return fail(NTGB_EINVAL, "ntgb_eval_host: C == NULL");
+    DeviceGuard dg(pb->device);
+    if (!dg.ok) return fail(NTGB_ECUDA, "cannot select device %d", pb->device);
+    const ntgb_dims &d = pb->dims;
+    const size_t P = (size_t)h->P;
+    auto &s = pb->hs;
+    if (!pb->hstream) CUDA_TRY(cudaStreamCreateWithFlags(&pb->hstream, cudaStreamNonBlocking));
+    const size_t jper = h->jac_layout == NTGB_JAC_DENSE ? (size_t)d.ncnln * d.nC
+                      : h->jac_layout == NTGB_JAC_BAND  ? (size_t)d.ncnln * d.sorder : 0;
+    if (h->P > s.P || (h->J && (s.jac_layout != h->jac_layout || s.Jbytes < P * jper * sizeof(double))) ||
+        (h->Z && !s.Z)) {
+        double **ptrs[] = {&s.C, &s.f, &s.g, &s.c, &s.J, &s.Z, &s.result};
+        for (double **pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
+        const size_t cap = P;
+        CUDA_TRY(cudaMalloc((void **)&s.C, cap * d.nC * sizeof(double)));
+        CUDA_TRY(cudaMalloc((void **)&s.f, cap * sizeof(double)));
+        CUDA_TRY(cudaMalloc((void **)&s.g, cap * d.nC * sizeof(double)));
+        CUDA_TRY(cudaMalloc((void **)&s.c, cap * (size_t)(d.ncnln > 0 ? d.ncnln : 1) * sizeof(double)));
+        CUDA_TRY(cudaMalloc((void **)&s.result, cap * 2 * sizeof(double)));
+        if (h->Z) CUDA_TRY(cudaMalloc((void **)&s.Z, cap * d.nZ * sizeof(double)));
+        s.Jbytes = 0;
+        if (h->J && jper) {
+            s.Jbytes = cap * jper * sizeof(double);
+            CUDA_TRY(cudaMalloc((void **)&s.J, s.Jbytes));
+            /* out-of-band entries are zeroed once, as the reference's calloc does (src/ntg.c:218) */
+            CUDA_TRY(cudaMemsetAsync(s.J, 0, s.Jbytes, pb->hstream));
+        }
+        s.P = (int)cap;
+        s.jac_layout = h->jac_layout;
+    }
+    CUDA_TRY(cudaMemcpyAsync(s.C, h->C, P * d.nC * sizeof(double), cudaMemcpyHostToDevice, pb->hstream));
+    ntgb_eval_args a = *h;
+    a.C = s.C;
+    a.f = h->f ? s.f : nullptr;
+    a.g = h->g ? s.g : nullptr;
+    a.c = h->c ? s.c : nullptr;
+    a.J = h->J ? s.J : nullptr;
+    a.Z = h->Z ? s.Z : nullptr;
+    a.result = h->result ? s.result : nullptr;
+    a.stream = pb->hstream;
+    const int rc = ntgb_eval(pb, &a);
+    if (rc) return rc;
+    const bool ov = h->mode_obj == 0 || h->mode_obj == 2, od = h->mode_obj == 1 || h->mode_obj == 2;
+    const bool cv = h->mode_con == 0 || h->mode_con == 2, cd = h->mode_con == 1 || h->mode_con == 2;
+    if (h->f && ov) CUDA_TRY(cudaMemcpyAsync(h->f, s.f, P * sizeof(double), cudaMemcpyDeviceToHost, pb->hstream));
+    if (h->g && od) CUDA_TRY(cudaMemcpyAsync(h->g, s.g, P * d.nC * sizeof(double), cudaMemcpyDeviceToHost, pb->hstream));
+    if (h->c && cv && d.ncnln) CUDA_TRY(cudaMemcpyAsync(h->c, s.c, P * d.ncnln * sizeof(double), cudaMemcpyDeviceToHost, pb->hstream));
+    if (h->J && cd && jper) CUDA_TRY(cudaMemcpyAsync(h->J, s.J, P * jper * sizeof(double), cudaMemcpyDeviceToHost, pb->hstream));
+    if (h->Z) CUDA_TRY(cudaMemcpyAsync(h->Z, s.Z, P * d.nZ * sizeof(double), cudaMemcpyDeviceToHost, pb->hstream));
+    if (h->result) CUDA_TRY(cudaMemcpyAsync(h->result, s.result, P * 2 * sizeof(double), cudaMemcpyDeviceToHost, pb->hstream));
+    CUDA_TRY(cudaStreamSynchronize(pb->hstream));
+    return 0;
+}
+
+int ntgb_eval_linear(ntgb_problem *pb, int P, const double *C, double *lin, double *viol, void *stream)
+{
+    if (!pb || !C) return fail(NTGB_EINVAL, "ntgb_eval_linear: null argument");
+    const int nclin = pb->dims.nclin;
+    if (P <= 0 || nclin == 0) return 0;
+    DeviceGuard dg(pb->device);
+    if (!dg.ok) return fail(NTGB_ECUDA, "cannot select device %d", pb->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (viol) CUDA_TRY(cudaMemsetAsync(viol, 0, sizeof(double) * (size_t)P, st));
+    const long long total = (long long)P * nclin;
+    const int block = 256;
+    const unsigned grid = (unsigned)((total + block - 1) / block);
+    k_linear<<<grid, block, 0, st>>>(pb->dAband, pb->dAcol0, pb->dlin_lb, pb->dlin_ub, nclin, pb->dims.nout,
+                                     pb->dims.sorder, pb->tab, P, C, lin, viol);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int ntgb_spline_interp(ntgb_problem *pb, int P, const double *C, int nt, const double *t, double *out, void *stream)
+{
+    if (!pb || !C || !t || !out) return fail(NTGB_EINVAL, "ntgb_spline_interp: null argument");
+    if (P <= 0 || nt <= 0) return 0;
+    DeviceGuard dg(pb->device);
+    if (!dg.ok) return fail(NTGB_ECUDA, "cannot select device %d", pb->device);
+    InterpDesc D;
+    D.nout = pb->dims.nout; D.nC = pb->dims.nC; D.nz = pb->dims.nz;
+    for (int j = 0; j < D.nout; j++) {
+        D.order[j] = pb->order[j]; D.mult[j] = pb->mult[j]; D.md[j] = pb->maxderiv[j];
+        D.ninterv[j] = pb->ninterv[j]; D.ncoef[j] = pb->ncoef[j];
+        D.iC[j] = pb->tab.iC[j]; D.iz[j] = pb->tab.iz[j];
+        D.aug[j] = pb->daug[j]; D.knots[j] = pb->dknots[j];
+    }
+    const long long total = (long long)P * nt * D.nout;
+    const int block = 128;
+    k_spline_interp<<<(unsigned)((total + block - 1) / block), block, 0, (cudaStream_t)stream>>>(D, P, C, nt, t, out);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+} /* extern "C" */

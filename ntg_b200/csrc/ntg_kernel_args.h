@@ -1,0 +1,42 @@
+/*
+ * ntg_kernel_args.h -- the POD block handed from the core library
+ * (ntg_core.cu) to a callback pack's launcher (ntg_eval_kernel.cuh).
+ * Internal: not part of the public ABI, but both sides are built from this
+ * header, and NTGB_KERNEL_ABI is checked at pack registration.
+ */
+#ifndef NTG_KERNEL_ARGS_H_
+#define NTG_KERNEL_ARGS_H_
+
+#include "ntg_b200.h"
+
+#define NTGB_KERNEL_ABI 3
+#define NTGB_MAXOUT 8      /* outputs per problem the device tables can describe */
+#define NTGB_MAXORDER 20   /* PGS bsplvb work arrays: jmax = 20   */
+
+/* Device-resident, batch-shared problem description (built once by K0). */
+typedef struct ntgb_devtab {
+    int nout, nbps, nC, nz, nZ, ncnln, S;
+    int nicf, nucf, nfcf, nnlic, nnltc, nnlfc;
+    int order[NTGB_MAXOUT], mult[NTGB_MAXOUT], maxderiv[NTGB_MAXOUT], ncoef[NTGB_MAXOUT];
+    int iC[NTGB_MAXOUT], iz[NTGB_MAXOUT], iZ[NTGB_MAXOUT], jk0[NTGB_MAXOUT];
+    /* active-variable masks per breakpoint class; bit d of avmask[cls][j] set
+     * <=> z[j][d] is computed there.  cls = (bp==0) | (bp==nbps-1)<<1.
+     * (updateZ only fills listed variables, reference src/colloc.c:344-367) */
+    unsigned avmask[4][NTGB_MAXOUT];
+    const double *Bt[NTGB_MAXOUT];  /* [(k*maxderiv+d)*nbps + bp]  breakpoint-fastest      */
+    const double *Bn[NTGB_MAXOUT];  /* [(bp*order+k)*maxderiv + d] reference block layout  */
+    const int *off[NTGB_MAXOUT];    /* [bp] block offset (reference src/colloc.c:108)      */
+    const double *bps;              /* [nbps]                                              */
+    const double *nl_lb, *nl_ub;    /* [nnlic+nnltc+nnlfc] compact nonlinear bounds        */
+    const int *col_lo, *col_hi;     /* [nC] first/last breakpoint whose band holds column  */
+} ntgb_devtab;
+
+typedef struct ntgb_launch {
+    int abi;
+    ntgb_devtab tab;
+    ntgb_eval_args args; /* device pointers */
+    int sm_count;
+    int max_smem_optin;  /* bytes */
+} ntgb_launch;
+
+#endif

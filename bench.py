@@ -1,0 +1,457 @@
+#!/usr/bin/env python
+"""bench.py -- collocation evals/sec (cost + constraints + Jacobian, batched)
+and % of the HBM roofline, on 1..8 B200 (BASELINE.json `metric`).
+
+    python bench.py --gpus N --steps K --warmup W [--workload cfg4] [--impl reference]
+
+One "step" = one pass of the hot path over one batch of synthetic coefficient
+vectors: a single launch of the fused evaluator K1 (funobj mode 2 + funcon
+mode 2 for every problem of the batch: cost, gradient, constraints, banded
+Jacobian) and, at N > 1, the NCCL all-gather of the per-problem
+(objective, violation) table.  Weak scaling: every rank evaluates its own
+batch of P problems (problems are independent; no data-path collective).
+
+Headline workload (DESIGN.md "Measurement"): CFG-4, the kincar MPC shape with
+64 breakpoints x 65536 problems -- the largest of BASELINE.json's configs the
+survey names as a 1-GPU roofline config; CFG-2/3/5 are
+reported beside it under "other_workloads" at N = 1.
+
+Rank 0 prints ONE JSON line.  `--impl reference` times the reference's own CPU
+implementation (oracle/_ref: the unmodified reference C sources) on all host
+cores for the same metric and config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from ntg_b200 import JAC_BAND, configs  # noqa: E402
+
+L2_BYTES = 126e6
+METRIC = "collocation_evals_per_sec"
+UNIT = "evals/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+# --------------------------------------------------------------------------- CPU reference arm
+def _ref_worker(args):
+    cfg, lo, hi, P, kind, shipped = args
+    from oracle.oracle import Oracle
+    spec, _ = configs.get(cfg)
+    X = configs.coefficients(cfg, P, spec)[lo:hi]
+    o = Oracle(kind, shipped_flags=shipped) if kind == "ref" else Oracle(kind)
+    t0 = time.perf_counter()
+    r = o.eval(spec, X, dense=False, band=False, outputs=False, reps=1)
+    return time.perf_counter() - t0, r["seconds"], hi - lo
+
+
+class CpuReference:
+    """The reference's CPU implementation of the path on the host cores: one
+    process per core (the reference is non-re-entrant: file-static globals,
+    src/ntg.c:17-41), disjoint slices of the sample."""
+
+    def __init__(self, cfg: str, cores: int | None = None):
+        from oracle import oracle
+        self.cfg = cfg
+        self.kind = "ref" if oracle.have_ref() else "port"
+        self.cores = cores or len(os.sched_getaffinity(0))
+        import multiprocessing as mp
+        self.pool = mp.get_context("spawn").Pool(self.cores)
+
+    def sample_size(self, target_seconds: float) -> int:
+        spec, P = configs.get(self.cfg)
+        # calibrate on one core
+        n0 = 4 if self.cfg == "cfg5" else 512
+        w, s, n = _ref_worker((self.cfg, 0, n0, n0, self.kind, False))
+        per_eval = max(s, 1e-9) / n
+        n_target = int(target_seconds * self.cores / per_eval)
+        per_core = max(1, min(n_target, P) // self.cores)
+        return per_core * self.cores
+
+    def step(self, nsample: int):
+        from ntg_b200.shard import shard_range
+        jobs = [(self.cfg, *shard_range(nsample, r, self.cores), nsample, self.kind, False)
+                for r in range(self.cores)]
+        t0 = time.perf_counter()
+        res = self.pool.map(_ref_worker, jobs)
+        wall = time.perf_counter() - t0
+        inner = max(r[1] for r in res)   # slowest worker, funcon+funobj time only
+        return wall, inner
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_baseline(cfg: str, target_seconds: float = 4.0):
+    ref = CpuReference(cfg)
+    try:
+        n = ref.sample_size(target_seconds)
+        ref.step(min(n, ref.cores * 2))  # warm the workers (imports, table build)
+        wall, inner = ref.step(n)
+        one = CpuReference(cfg, cores=1)
+        n1 = max(1, n // ref.cores)
+        one.step(1)
+        _, inner1 = one.step(n1)
+        one.close()
+        spec, P = configs.get(cfg)
+        return {"value": n / inner, "unit": UNIT, "cores": ref.cores,
+                "kind": "reference" if ref.kind == "ref" else "port",
+                "sample": f"{n} of {P} problems of {spec.name} (same seeded coefficients), one process per "
+                          f"core, -O2 -ffp-contract=off; funobj mode 2 + funcon mode 2 per problem",
+                "value_1core": n1 / inner1, "wall_value": n / wall}
+    finally:
+        ref.close()
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    ref = CpuReference(a.workload)
+    spec, P = configs.get(a.workload)
+    n = ref.sample_size(a.ref_step_seconds)
+    for _ in range(max(a.warmup, 1)):
+        ref.step(n)
+    t, tw = [], []
+    for _ in range(a.steps):
+        wall, inner = ref.step(n)
+        t.append(inner)   # slowest worker's time inside funcon+funobj: the path itself,
+        tw.append(wall)   # without this harness's process dispatch and input generation
+    ref.close()
+    per_step = float(np.mean(t))
+    value = n / per_step
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(a.workload, spec, P, a.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores,
+                         "kind": "reference" if ref.kind == "ref" else "port",
+                         "sample": f"each step = {n} of {P} problems of {spec.name}, one process per core, "
+                                   f"step time = slowest worker's time inside funcon+funobj",
+                         "wall_value": n / float(np.mean(tw))},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(cfg, spec, P, ngpus):
+    return {"workload": spec.name, "cfg": cfg, "problems_per_gpu": P, "total_problems": P * ngpus,
+            "nout": spec.nout, "nbps": spec.nbps, "order": spec.order[0], "nC": spec.nC,
+            "ncnln": spec.ncnln, "jacobian": "band-compact",
+            "bytes_per_eval": spec.bytes_per_eval(), "parallelism": f"problem-sharded x{ngpus}",
+            "variant": None, "l2": None}
+
+
+# --------------------------------------------------------------------------- GPU arm
+def time_workload(torch, pb, spec, cfg, P, steps, warmup, dist=None, world=1, use_graph=False):
+    """-> dict(ms_per_step, kernel_ms, launches).  Ring of buffer sets larger than L2 when one
+    set is not."""
+    dev = torch.device("cuda", pb.device)
+    per_set = P * spec.bytes_per_eval()
+    nset = 1 if per_set >= 2 * L2_BYTES else min(64, int(np.ceil(2 * L2_BYTES / per_set)))
+    X0 = torch.from_numpy(configs.coefficients(cfg, P, spec)).to(dev)
+    sets = [(X0.clone() if i else X0, pb.alloc_outputs(P, JAC_BAND, zero=False)) for i in range(nset)]
+    stream = torch.cuda.current_stream(dev)
+    args = [pb.eval_args(x, o, 2, 2, JAC_BAND, 0, stream.cuda_stream) for x, o in sets]
+    gathered = [torch.empty((world * P, 2), dtype=torch.float64, device=dev) for _ in range(nset)] if dist else None
+
+    graphs = None
+    if use_graph and dist is None:
+        for i in range(nset):
+            pb.launch(args[i])
+        torch.cuda.synchronize(dev)
+        graphs = []
+        for i in range(nset):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                cap = pb.eval_args(sets[i][0], sets[i][1], 2, 2, JAC_BAND, 0,
+                                   torch.cuda.current_stream(dev).cuda_stream)
+                pb.launch(cap)
+            graphs.append(g)
+
+    def step(i):
+        s = i % nset
+        if graphs is not None:
+            graphs[s].replay()
+        else:
+            pb.launch(args[s])
+        if dist is not None:
+            dist.all_gather_into_tensor(gathered[s], sets[s][1]["result"])
+
+    for i in range(warmup):
+        step(i)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for i in range(steps):
+        s = i % nset
+        ev[i][0].record()
+        if graphs is not None:
+            graphs[s].replay()
+        else:
+            pb.launch(args[s])
+        ev[i][1].record()
+        if dist is not None:
+            dist.all_gather_into_tensor(gathered[s], sets[s][1]["result"])
+    e1.record()
+    torch.cuda.synchronize(dev)
+    if dist is not None:
+        dist.barrier()
+    total_ms = e0.elapsed_time(e1)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    chk = float(sets[0][1]["result"][:, 0].sum().item())
+    assert np.isfinite(chk), "non-finite objective in the timed run"
+    return {"ms_per_step": total_ms / steps, "kernel_ms": kernel_ms, "launches": steps, "nset": nset,
+            "footprint_mb": per_set * nset / 1e6}
+
+
+def time_e2e(torch, pb, spec, cfg, P, steps, warmup, full: bool):
+    """Same metric through the C ABI with HOST buffers: every step copies that step's
+    coefficients from pinned host memory, evaluates, and copies results back to pinned host
+    memory.  full=True: f, g, c and the whole Jacobian band come back (what a host-side
+    consumer such as NPSOL needs).  full=False: only the per-problem (objective, violation)
+    table comes back; g, c, J stay resident for a GPU-side consumer (they are still computed
+    and written to HBM).  The batch is pipelined in chunks over two streams so copies overlap
+    compute."""
+    dev = torch.device("cuda", pb.device)
+    d = pb.dims
+    nchunk = 8 if P >= 8192 else 1
+    Pc = P // nchunk
+    Xh = torch.from_numpy(configs.coefficients(cfg, P, spec)).pin_memory()
+    host = {"f": torch.empty(P, dtype=torch.float64).pin_memory(),
+            "result": torch.empty((P, 2), dtype=torch.float64).pin_memory()}
+    if full:
+        host.update(g=torch.empty((P, d.nC), dtype=torch.float64).pin_memory(),
+                    c=torch.empty((P, d.ncnln), dtype=torch.float64).pin_memory(),
+                    J=torch.empty((P, d.ncnln * d.sorder), dtype=torch.float64).pin_memory())
+    streams = [torch.cuda.Stream(dev) for _ in range(2)]
+    bufs = []
+    for s in range(2):
+        with torch.cuda.stream(streams[s]):
+            bufs.append((torch.empty((Pc, d.nC), dtype=torch.float64, device=dev),
+                         pb.alloc_outputs(Pc, JAC_BAND, zero=False)))
+    keys = ["f", "result"] + (["g", "c", "J"] if full else [])
+    h2d = P * d.nC * 8
+    d2h = sum(host[k].numel() * 8 for k in keys)
+
+    def one_step():
+        for ci in range(nchunk):
+            s = ci % 2
+            st = streams[s]
+            lo, hi = ci * Pc, (ci + 1) * Pc
+            with torch.cuda.stream(st):
+                xd, out = bufs[s]
+                xd.copy_(Xh[lo:hi], non_blocking=True)
+                pb.launch(pb.eval_args(xd, out, 2, 2, JAC_BAND, 0, st.cuda_stream))
+                for k in keys:
+                    src = out[k] if k != "c" else out["c"][:, :d.ncnln]
+                    host[k][lo:hi].copy_(src, non_blocking=True)
+        for st in streams:
+            st.synchronize()
+
+    for _ in range(warmup):
+        one_step()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    torch.cuda.synchronize(dev)
+    dt = (time.perf_counter() - t0) / steps
+    assert np.isfinite(float(host["f"].sum())), "non-finite objective in the e2e run"
+    return {"value": P / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "ms_per_step": dt * 1e3, "launches_per_step": nchunk,
+            "what": ("all outputs (f, g, c, Jacobian band) to pinned host memory" if full else
+                     "(objective, violation) table to host; g, c, J computed and left resident in HBM")}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg4", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--variant", default=os.environ.get("NTG_BENCH_VARIANT", "fast"), choices=["exact", "fast"])
+    ap.add_argument("--problems", type=int, default=0, help="override problems per GPU")
+    ap.add_argument("--no-others", action="store_true", help="skip the other workloads / baselines")
+    ap.add_argument("--ref-step-seconds", type=float, default=1.0)
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+
+    if a.impl == "reference":
+        return run_reference_arm(a)
+
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the evaluator has no CPU fallback "
+                         "(use --impl reference for the CPU reference arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from ntg_b200 import Problem
+
+    spec, P = configs.get(a.workload)
+    if a.problems:
+        P = a.problems
+    fast = a.variant == "fast"
+    pb = Problem(spec, local, fast=fast)
+    peak, peak_src = measured_peaks()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    r = time_workload(torch, pb, spec, a.workload, P, a.steps, a.warmup, dist, world)
+    clocks = sampler.stop() if sampler else None
+
+    ms = torch.tensor([r["ms_per_step"], r["kernel_ms"]], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step, ms_kernel = float(ms[0]), float(ms[1])
+    value = world * P / (ms_step * 1e-3)
+
+    e2e = time_e2e(torch, pb, spec, a.workload, P, max(3, min(a.steps, 10)), 3, full=True)
+    e2e_res = time_e2e(torch, pb, spec, a.workload, P, max(3, min(a.steps, 10)), 3, full=False)
+    if dist is not None:
+        t = torch.tensor([e2e["value"], e2e_res["value"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        e2e["value"], e2e_res["value"] = float(t[0]) * world, float(t[1]) * world
+
+    others = {}
+    if rank == 0 and world == 1 and not a.no_others:
+        for cfg in ("cfg2", "cfg3", "cfg4", "cfg5"):
+            if cfg == a.workload:
+                continue
+            s2, P2 = configs.get(cfg)
+            pb2 = Problem(s2, local, fast=fast)
+            small = cfg in ("cfg2", "cfg3")
+            st = 200 if small else (5 if cfg == "cfg5" else 20)
+            r2 = time_workload(torch, pb2, s2, cfg, P2, st, 5, use_graph=small)
+            gbs = P2 * s2.bytes_per_eval() / (r2["kernel_ms"] * 1e-3) / 1e9
+            others[cfg] = {"workload": s2.name, "problems": P2, "evals_per_s": P2 / (r2["ms_per_step"] * 1e-3),
+                           "ms_per_step": r2["ms_per_step"], "kernel_ms": r2["kernel_ms"],
+                           "algorithmic_gbs": gbs, "roofline_frac": gbs / peak,
+                           "launch": "cuda graph replay" if small else "stream launch",
+                           "l2": f"ring of {r2['nset']} buffer sets, {r2['footprint_mb']:.0f} MB"}
+            pb2.close()
+            torch.cuda.empty_cache()
+
+    if rank == 0:
+        bytes_launch = P * spec.bytes_per_eval()
+        ach = bytes_launch / (ms_kernel * 1e-3) / 1e9
+        cfgd = workload_config(a.workload, spec, P, world)
+        cfgd["variant"] = ("fast (FMA contraction allowed)" if fast else
+                           "exact (-fmad=false, reference summation order, bit-identical to the CPU reference)")
+        cfgd["l2"] = (f"inputs+outputs of one step = {r['footprint_mb']:.0f} MB over a ring of {r['nset']} "
+                      f"buffer set(s), larger than the 126 MB L2")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfgd, "clocks": clocks,
+            "e2e": e2e, "e2e_resident": e2e_res, "gpu_launches": r["launches"],
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "ntgb::ntg_eval_kernel<kincar>",
+                         "kernel_ms": ms_kernel, "algorithmic_bytes_per_launch": bytes_launch},
+            "other_workloads": others,
+        }
+        tr = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tr):
+            try:
+                line["roofline"]["traffic"] = json.load(open(tr)).get(a.workload)
+            except Exception:
+                pass
+        if world == 1 and not a.no_others:
+            line["cpu_baseline"] = cpu_baseline(a.workload)
+        print(json.dumps(line), flush=True)
+    pb.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -32,7 +32,7 @@ def core() -> C.CDLL:
         if not os.path.exists(path):
             raise NtgError(f"{path} is missing: build it with `python -m ntg_b200.build` "
                            "(nvcc, sm_100a).  There is no CPU fallback.")
-        lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        lib = C.CDLL(path)  # RTLD_LOCAL: it exports ntg(), linspace(), ... like the reference does
         lib.ntgb_last_error.restype = C.c_char_p
         lib.ntgb_version.restype = C.c_char_p
         lib.ntgb_find_pack.restype = C.POINTER(NtgbPack)
@@ -61,7 +61,7 @@ def load_pack(name: str) -> C.CDLL:
         path = os.path.join(_LIBDIR, f"libntgpack_{name}.so")
         if not os.path.exists(path):
             raise NtgError(f"callback pack {path} is missing: build it with `python -m ntg_b200.build`")
-        _packs[name] = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        _packs[name] = C.CDLL(path)  # RTLD_LOCAL: exact/fast variants define the same symbols
         if not core().ntgb_find_pack(name.encode()):
             raise NtgError(f"pack '{name}' loaded but did not register")
     return _packs[name]

@@ -140,3 +140,45 @@ class Oracle:
         if linear:
             r.update(A=A[:, :spec.nclin].T.copy(), bl=bl, bu=bu)  # A as [nclin][nC]
         return r
+
+
+SHIM_SO = os.path.join(HERE, "libnpsol_shim.so")
+
+
+def _run_main(shimlib, main_ptr, X: np.ndarray, mode_obj: int, mode_con: int, ncnln: int = 0):
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    P, n = X.shape
+    f = np.zeros(P)
+    g = np.zeros((P, n))
+    c = np.zeros((P, max(ncnln, 1)))
+    Jd = np.zeros((P, n, max(ncnln, 1))) if ncnln else None
+    dims = (C.c_int * 3)()
+    A = np.zeros((n, 64))
+    bl = np.zeros(n + 64 + ncnln)
+    bu = np.zeros(n + 64 + ncnln)
+    shimlib.shim_run_main.restype = C.c_int
+    calls = shimlib.shim_run_main(C.c_void_p(main_ptr), P, _dp(X), mode_obj, mode_con, _dp(f), _dp(g),
+                                  _dp(c), _dp(Jd), _dp(A), _dp(bl), _dp(bu), dims)
+    n_, nclin, ncn = dims[0], dims[1], dims[2]
+    return dict(calls=calls, f=f, g=g, c=c[:, :ncn], Jdense=Jd, n=n_, nclin=nclin, ncnln=ncn,
+                A=A.reshape(-1)[:n_ * nclin].reshape(n_, nclin).T.copy() if nclin else None,
+                bl=bl[:n_ + nclin + ncn], bu=bu[:n_ + nclin + ncn])
+
+
+def run_reference_example(name: str, X: np.ndarray, mode_obj: int = 2, mode_con: int = 2):
+    """Run the reference's UNMODIFIED examples/<name>.c main() (built into
+    oracle/_ref/libref_<name>.so) linked against the unmodified reference
+    library; its ntg() call lands in the fake npsol_ which evaluates batch X."""
+    ex = C.CDLL(os.path.join(HERE, "_ref", f"libref_{name}.so"))
+    ref = C.CDLL(REF_SO)
+    main = C.cast(getattr(ex, f"ref_{name}_main"), C.c_void_p).value
+    return _run_main(ref, main, X, mode_obj, mode_con)
+
+
+def run_product_main(main_ptr: int, X: np.ndarray, mode_obj: int = 2, mode_con: int = 2, ncnln: int = 0):
+    """Run a user program's main() that calls THIS repo's ntg(): the fake NPSOL
+    is made visible process-wide (RTLD_GLOBAL) so ntg()'s dlsym finds it."""
+    if not os.path.exists(SHIM_SO):
+        build("port")
+    shim = C.CDLL(SHIM_SO, mode=C.RTLD_GLOBAL)
+    return _run_main(shim, main_ptr, X, mode_obj, mode_con, ncnln)

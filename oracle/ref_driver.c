@@ -24,142 +24,7 @@
 
 #include "ntg.h"      /* the reference's own header (-I/root/reference/src) */
 #include "ntg_b200.h" /* ntgb_setup: same fields as ntg()'s arguments        */
-
-typedef struct {
-    int P;
-    const double *X; /* [P][n] */
-    int mode_obj, mode_con;
-    double *f;       /* [P]            */
-    double *g;       /* [P][n]         */
-    double *c;       /* [P][ncnln]     */
-    double *Jdense;  /* [P][ncnln*n] column-major per problem, NaN = unwritten */
-    double *Jband;   /* [P][ncnln][S]  row-major band values                   */
-    const int *col0; /* [ncnln][nout]  first column of each output band        */
-    const int *order;
-    int nout, S;
-    long pattern_bad; /* written-outside-band + unwritten-inside-band entries  */
-    double *A;        /* [nclin*n] column-major copy of NPSOL's A              */
-    double *bl, *bu;  /* [n+nclin+ncnln]                                       */
-    int reps;
-    double best_seconds;
-    int n, nclin, ncnln;
-} ref_request;
-
-static ref_request *g_req;
-
-static double now_s(void)
-{
-    struct timespec ts;
-    clock_gettime(CLOCK_MONOTONIC, &ts);
-    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
-}
-
-void npoptn_(char *option, long len)
-{
-    (void)option;
-    (void)len;
-}
-
-typedef void (*funcon_t)(int *, int *, int *, int *, int *, double *, double *, double *, int *);
-typedef void (*funobj_t)(int *, int *, double *, double *, double *, int *);
-
-static long check_pattern(const ref_request *r, const double *cJac, int ldJ)
-{
-    long bad = 0;
-    int row, col, j, k;
-    char *inband = malloc((size_t)r->n);
-    for (row = 0; row < r->ncnln; row++) {
-        memset(inband, 0, (size_t)r->n);
-        for (j = 0; j < r->nout; j++)
-            for (k = 0; k < r->order[j]; k++)
-                inband[r->col0[row * r->nout + j] + k] = 1;
-        for (col = 0; col < r->n; col++) {
-            int written = !isnan(cJac[(size_t)col * ldJ + row]);
-            if (written != inband[col])
-                bad++;
-        }
-    }
-    free(inband);
-    return bad;
-}
-
-void npsol_(int *n_, int *nclin_, int *ncnln_, int *ldA, int *ldJ_, int *ldR, double *A,
-            double *bl, double *bu, funcon_t funcon, funobj_t funobj, int *inform,
-            int *iter, int *istate, double *c, double *cJac, double *clambda, double *f,
-            double *g, double *R, double *x, int *iw, int *leniw, double *w, int *lenw)
-{
-    ref_request *r = g_req;
-    int n = *n_, nclin = *nclin_, ncnln = *ncnln_, ldJ = *ldJ_;
-    int rep, p, i, j, k;
-    int *needc;
-    (void)ldR; (void)istate; (void)clambda; (void)R; (void)iw; (void)leniw; (void)w; (void)lenw;
-    (void)ldA;
-    *inform = 0;
-    *iter = 0;
-    if (r == NULL)
-        return;
-    r->n = n; r->nclin = nclin; r->ncnln = ncnln;
-    if (r->A && nclin > 0)
-        memcpy(r->A, A, sizeof(double) * (size_t)nclin * n);
-    if (r->bl) memcpy(r->bl, bl, sizeof(double) * (size_t)(n + nclin + ncnln));
-    if (r->bu) memcpy(r->bu, bu, sizeof(double) * (size_t)(n + nclin + ncnln));
-
-    needc = malloc(sizeof(int) * (size_t)(ncnln > 0 ? ncnln : 1));
-    for (i = 0; i < ncnln; i++) needc[i] = 1;
-
-    if (ncnln > 0 && (r->Jdense || r->Jband))
-        for (i = 0; i < ldJ * n; i++) cJac[i] = NAN;
-
-    r->best_seconds = 1e300;
-    r->pattern_bad = 0;
-    for (rep = 0; rep < (r->reps > 0 ? r->reps : 1); rep++) {
-        double acc = 0.0;
-        for (p = 0; p < r->P; p++) {
-            int nstate = (rep == 0 && p == 0) ? 1 : 0;
-            int mode;
-            double t0;
-            memcpy(x, r->X + (size_t)p * n, sizeof(double) * (size_t)n);
-            t0 = now_s();
-            if (ncnln > 0 && r->mode_con >= 0) {
-                mode = r->mode_con;
-                funcon(&mode, &ncnln, &n, &ldJ, needc, x, c, cJac, &nstate);
-            }
-            if (r->mode_obj >= 0) {
-                mode = r->mode_obj;
-                funobj(&mode, &n, x, f, g, &nstate);
-            }
-            acc += now_s() - t0;
-            if (rep > 0) continue;
-            if (r->mode_obj >= 0) {
-                if (r->f && r->mode_obj != 1) r->f[p] = *f;
-                if (r->g && r->mode_obj != 0) memcpy(r->g + (size_t)p * n, g, sizeof(double) * (size_t)n);
-            }
-            if (ncnln > 0 && r->mode_con >= 0) {
-                if (r->c && r->mode_con != 1)
-                    memcpy(r->c + (size_t)p * ncnln, c, sizeof(double) * (size_t)ncnln);
-                if (r->mode_con != 0) {
-                    if (r->Jdense)
-                        memcpy(r->Jdense + (size_t)p * ncnln * n, cJac,
-                               sizeof(double) * (size_t)ncnln * n);
-                    if (r->Jband) {
-                        double *dst = r->Jband + (size_t)p * ncnln * r->S;
-                        for (i = 0; i < ncnln; i++) {
-                            int s = 0;
-                            for (j = 0; j < r->nout; j++)
-                                for (k = 0; k < r->order[j]; k++, s++)
-                                    dst[(size_t)i * r->S + s] =
-                                        cJac[(size_t)(r->col0[i * r->nout + j] + k) * ldJ + i];
-                        }
-                    }
-                    if ((r->Jdense || r->Jband) && (p == 0 || p == r->P - 1))
-                        r->pattern_bad += check_pattern(r, cJac, ldJ);
-                }
-            }
-        }
-        if (acc < r->best_seconds) r->best_seconds = acc;
-    }
-    free(needc);
-}
+#include "npsol_shim.h"
 
 /* Jacobian row pattern from the reference's OWN tables (public symbols of
  * src/colloc.c): rows [0,nnlic) use column iC[j] (CollocConcatMultI,
@@ -250,7 +115,7 @@ int ref_eval(const ntgb_setup *s, int P, const double *X, int mode_obj, int mode
              double *g, double *c, double *Jdense, double *Jband, long *pattern_bad, double *A,
              double *bl, double *bu, int reps, double *seconds)
 {
-    ref_request req;
+    shim_request req;
     ntgb_dims d;
     int *col0 = NULL;
     double *x;
@@ -277,7 +142,8 @@ int ref_eval(const ntgb_setup *s, int P, const double *X, int mode_obj, int mode
     clambda = calloc((size_t)(d.nC + d.nclin + d.ncnln), sizeof(double));
     R = calloc((size_t)(d.nC + 1) * (d.nC + 1), sizeof(double));
 
-    g_req = &req;
+    req.nan_fill = 1;
+    shim_set_request(&req);
     /* the reference prints its banner on every ntg() call (src/ntg.c:161):
      * silence stdout for the duration */
     {
@@ -300,7 +166,7 @@ int ref_eval(const ntgb_setup *s, int P, const double *X, int mode_obj, int mode
         stdout = keep;
         if (devnull) fclose(devnull);
     }
-    g_req = NULL;
+    shim_set_request(NULL);
     if (pattern_bad) *pattern_bad = req.pattern_bad;
     if (seconds) *seconds = req.best_seconds;
     free(col0); free(x); free(istate); free(clambda); free(R);

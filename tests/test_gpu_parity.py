@@ -1,0 +1,216 @@
+"""Parity tests proper: the CUDA path (through the C ABI, libntg_b200.so + a
+callback pack) against the CPU oracle and the committed golden vectors.
+
+Bar (BASELINE.json north_star): knot-interval indices and Jacobian sparsity
+pattern bit-exact; flat outputs, cost, gradient, constraints, Jacobian within
+1e-12 relative / 1e-14 absolute (scaled by the vector's infinity norm).
+The "exact" pack variant (-fmad=false, reference summation order) is held to
+the stronger bar of bit-identity wherever no libm call is involved.
+"""
+import numpy as np
+import pytest
+
+from common import (GOLDEN_CASES, assert_bitexact, assert_close, golden_spec, load_golden, violation)
+from ntg_b200 import JAC_BAND, JAC_DENSE, configs
+
+pytestmark = pytest.mark.gpu
+
+NO_LIBM = {"cfg2_vanderpol", "cfg3_kincar", "cfg4_kincar64", "cfg5_syn6", "syn6_small"}
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def gpu_eval(torch, spec, X, fast, jac=JAC_BAND, want_Z=False, mode_obj=2, mode_con=2):
+    from ntg_b200 import Problem
+    pb = Problem(spec, 0, fast=fast)
+    o = pb.eval(torch.from_numpy(np.ascontiguousarray(X)).cuda(), mode_obj, mode_con, jac, want_Z)
+    torch.cuda.synchronize()
+    r = {k: (None if v is None else v.cpu().numpy()) for k, v in o.items()}
+    r["c"] = r["c"][:, :spec.ncnln]
+    if r["J"] is not None and jac == JAC_BAND:
+        r["Jband"] = pb.band_to_rows(r["J"])
+    return pb, r
+
+
+@pytest.mark.parametrize("fast", [False, True], ids=["exact", "fast"])
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_against_golden_vectors(torch_cuda, name, fast):
+    """golden = outputs of the UNMODIFIED reference on seeded inputs"""
+    spec, X = golden_spec(name)
+    g = load_golden(name)
+    pb, r = gpu_eval(torch_cuda, spec, X, fast)
+    B, off, _ = pb.tables()
+    for j, b in enumerate(B):
+        assert_bitexact(b, g["B"][j], f"{name}: K0 table of output {j}")
+    assert_bitexact(off, g["off"], f"{name}: knot-interval offsets")
+    col0, _ = pb.pattern()
+    assert_bitexact(col0, g["col0"], f"{name}: Jacobian sparsity pattern")
+    cmp = assert_bitexact if (not fast and name in NO_LIBM) else assert_close
+    cmp(r["f"], g["f"], f"{name}: objective")
+    cmp(r["g"], g["g"], f"{name}: gradient")
+    cmp(r["c"], g["c"], f"{name}: constraints")
+    cmp(r["Jband"], g["Jband"], f"{name}: Jacobian band")
+    assert_bitexact(pb.linear(), g["A"], f"{name}: linear constraint matrix A")
+    bl, bu = pb.bounds()
+    assert_bitexact(bl, g["bl"], "bl")
+    assert_bitexact(bu, g["bu"], "bu")
+    pb.close()
+
+
+@pytest.mark.parametrize("fast", [False, True], ids=["exact", "fast"])
+@pytest.mark.parametrize("cfg,P", [("cfg2", 4096), ("cfg3", 8192), ("cfg4", 4096), ("cfg5", 64)])
+def test_against_oracle_at_baseline_sizes(torch_cuda, port, cfg, P, fast):
+    """full batch for CFG-2/3, 4096-problem subset for CFG-4,
+    64-problem subset for CFG-5."""
+    spec, _ = configs.get(cfg)
+    X = configs.coefficients(cfg, P, spec)
+    o = port.eval(spec, X, dense=False, band=True)
+    pb, r = gpu_eval(torch_cuda, spec, X, fast)
+    cmp = assert_bitexact if not fast else assert_close
+    for k, ok in (("f", "f"), ("g", "g"), ("c", "c"), ("Jband", "Jband")):
+        cmp(r[k], o[ok], f"{cfg}.{k}")
+    assert_bitexact(r["result"][:, 0], r["f"], "result[:,0] is the objective")
+    assert_close(r["result"][:, 1], violation(spec, o["c"]), "max nonlinear constraint violation")
+    pb.close()
+
+
+@pytest.mark.parametrize("name", ["cfg2_vanderpol", "cfg4_kincar64", "endpoint"])
+def test_dense_npsol_layout_and_unwritten_zeros(torch_cuda, port, name):
+    """NPSOL's column-major ncnln x nC Jacobian: band entries equal the oracle's,
+    everything the reference never writes stays at the allocation-time zero."""
+    spec, X = golden_spec(name)
+    o = port.eval(spec, X, dense=True, band=False)
+    pb, r = gpu_eval(torch_cuda, spec, X, False, jac=JAC_DENSE)
+    written = ~np.isnan(o["Jdense"])
+    assert np.all(r["J"][~written] == 0.0), "wrote outside the reference's sparsity pattern"
+    cmp = assert_bitexact if name in NO_LIBM else assert_close
+    cmp(r["J"][written], o["Jdense"][written], "dense Jacobian band entries")
+    pb.close()
+
+
+@pytest.mark.parametrize("name", ["cfg3_kincar", "endpoint"])
+def test_flat_outputs_Z(torch_cuda, port, name):
+    """Z[p][iZ_j + bp*maxderiv_j + d] equals updateZ over the union of active variables"""
+    spec, X = golden_spec(name)
+    pb, r = gpu_eval(torch_cuda, spec, X, False, want_Z=True)
+    for p in range(X.shape[0]):
+        Z = np.zeros(spec.nZ)
+        for kind, lists in ((0, (spec.initialcostav if spec.nicf else [], spec.initialconstrav if spec.nnlic else [])),
+                            (1, (spec.trajectorycostav if spec.nucf else [], spec.trajectoryconstrav if spec.nnltc else [])),
+                            (2, (spec.finalcostav if spec.nfcf else [], spec.finalconstrav if spec.nnlfc else []))):
+            for av in lists:
+                if len(av):
+                    Zk = port.updateZ(spec, X[p], list(av), kind)
+                    Z = np.where(Zk != 0, Zk, Z)
+        assert_bitexact(r["Z"][p], Z, f"{name}: flat outputs of problem {p}")
+    pb.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_modes(torch_cuda, port, mode):
+    """mode 0 values only, 1 derivatives only, 2 both; -1 skips a half"""
+    spec, X = golden_spec("endpoint")
+    full = port.eval(spec, X, dense=False)
+    pb, r = gpu_eval(torch_cuda, spec, X, False, mode_obj=mode, mode_con=mode)
+    if mode != 1:
+        assert_close(r["f"], full["f"], "f")
+        assert_close(r["c"], full["c"], "c")
+    else:
+        assert np.all(r["f"] == 0) and np.all(r["c"] == 0), "mode 1 must not write values"
+    if mode != 0:
+        assert_close(r["g"], full["g"], "g")
+        assert_close(r["Jband"], full["Jband"], "J")
+    else:
+        assert np.all(r["g"] == 0) and np.all(r["J"] == 0), "mode 0 must not write derivatives"
+    pb.close()
+    pb, r = gpu_eval(torch_cuda, spec, X, False, mode_obj=2, mode_con=-1)
+    assert_close(r["g"], full["g"], "g with constraints skipped")
+    assert np.all(r["c"] == 0) and np.all(r["J"] == 0)
+    pb.close()
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 11, 12, 13, 255, 257, 1000])
+def test_ragged_batches(torch_cuda, port, P):
+    """batch sizes around the tile size G (12 problems per CTA at nbps = 20), incl. P = 1"""
+    spec, _ = configs.get("cfg3")
+    X = configs.coefficients("cfg3", P, spec, seed=P)
+    o = port.eval(spec, X, dense=False)
+    pb, r = gpu_eval(torch_cuda, spec, X, False)
+    for k in ("f", "g", "c", "Jband"):
+        assert_bitexact(r[k], o[k], f"P={P}: {k}")
+    pb.close()
+
+
+def test_batch_independence_and_full_size_properties(torch_cuda):
+    """At BASELINE.json's full CFG-4 size (65536 x 64 breakpoints): results do not depend on
+    how the batch is sliced, a permuted batch gives the permuted result, and repeated
+    launches are bit-identical (no atomics on the data path)."""
+    torch = torch_cuda
+    from ntg_b200 import Problem
+    spec, P = configs.get("cfg4")
+    X = torch.from_numpy(configs.coefficients("cfg4", P, spec)).cuda()
+    pb = Problem(spec, 0, fast=True)
+    a = pb.eval(X)
+    b = pb.eval(X)
+    for k in ("f", "g", "c", "J", "result"):
+        assert torch.equal(a[k], b[k]), f"{k}: launch-to-launch nondeterminism"
+    perm = torch.randperm(P, device="cuda", generator=torch.Generator("cuda").manual_seed(5))
+    c = pb.eval(X[perm].contiguous())
+    for k in ("f", "g", "c", "J"):
+        assert torch.equal(c[k], a[k][perm]), f"{k}: depends on position in the batch"
+    lo, hi = 12345, 12345 + 1001
+    d = pb.eval(X[lo:hi].contiguous())
+    for k in ("f", "g", "c", "J"):
+        assert torch.equal(d[k], a[k][lo:hi]), f"{k}: depends on batch slicing"
+    # z is linear in C and the kincar cost is quadratic: f(2C) = 4 f(C), g(2C) = 2 g(C)
+    # (exact in binary floating point: scaling by 2 commutes with every rounding)
+    e = pb.eval((2.0 * X).contiguous())
+    assert torch.equal(e["f"], 4.0 * a["f"]) and torch.equal(e["g"], 2.0 * a["g"])
+    pb.close()
+
+
+def test_eval_host_path_matches_device_path(torch_cuda, port):
+    """ntgb_eval_host (host buffers, H2D/D2H inside) == ntgb_eval on device buffers"""
+    from ntg_b200 import Problem
+    spec, X = golden_spec("endpoint")
+    o = port.eval(spec, X, dense=True, band=True)
+    pb = Problem(spec, 0)
+    for jac, key in ((JAC_BAND, "Jband"), (JAC_DENSE, "Jdense")):
+        h = pb.eval_host(X, jac=jac, want_Z=False)
+        assert_close(h["f"], o["f"], "f")
+        assert_close(h["g"], o["g"], "g")
+        assert_close(h["c"], o["c"], "c")
+        if jac == JAC_BAND:
+            assert_close(pb.band_to_rows(h["J"]), o["Jband"], "band J")
+        else:
+            assert_close(h["J"], np.nan_to_num(o["Jdense"], nan=0.0), "dense J")
+        assert_close(h["result"][:, 1], violation(spec, o["c"]), "violation")
+    # growing and shrinking batches reuse / regrow the scratch
+    for P in (1, 40, 3):
+        Xp = np.random.default_rng(P).uniform(-1, 1, (P, spec.nC))
+        assert_close(pb.eval_host(Xp)["g"], port.eval(spec, Xp, dense=False, band=False)["g"], f"P={P}")
+    pb.close()
+
+
+def test_error_paths_on_gpu(torch_cuda):
+    from ntg_b200 import Problem
+    from ntg_b200.problem import NtgError
+    import torch
+    spec, _ = configs.get("cfg2")
+    pb = Problem(spec, 0)
+    X = torch.zeros((4, spec.nC), dtype=torch.float64, device="cuda")
+    out = pb.alloc_outputs(4)
+    with pytest.raises(NtgError, match="mode"):
+        pb.launch(pb.eval_args(X, out, mode_obj=5))
+    a = pb.eval_args(X, out)
+    a.C = None
+    with pytest.raises(NtgError, match="C == NULL"):
+        pb.launch(a)
+    with pytest.raises(NtgError, match="device"):
+        Problem(spec, 99)
+    pb.close()

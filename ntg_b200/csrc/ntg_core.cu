@@ -292,7 +292,7 @@ void host_band_row(const ntgb_problem *pb, const double *dz, int bp, double *ban
 extern "C" {
 
 const char *ntgb_last_error(void) { return g_err.c_str(); }
-const char *ntgb_version(void) { return "ntg_b200 0.1 (sm_100a, kernel ABI 3)"; }
+const char *ntgb_version(void) { return "ntg_b200 0.1 (sm_100a, kernel ABI 4)"; }
 
 int ntgb_register_pack(const ntgb_pack *pack)
 {
@@ -494,6 +494,32 @@ int ntgb_create(ntgb_problem **out, const ntgb_setup *s, int device)
         if ((rc = dev_upload(pb, &dlo, lo.data(), (size_t)T.nC))) return rc;
         if ((rc = dev_upload(pb, &dhi, hi.data(), (size_t)T.nC))) return rc;
         T.col_lo = dlo; T.col_hi = dhi;
+        /* runs of equal offset per output, and the run each column's gather starts in */
+        std::vector<int> seg0(T.nC, 0);
+        for (int j = 0; j < nout; j++) {
+            std::vector<int> st, so;
+            for (int bp = 0; bp < nbps; bp++) {
+                const int o = pb->hoff[(size_t)j * nbps + bp];
+                if (bp == 0 || o != so.back()) { st.push_back(bp); so.push_back(o); }
+            }
+            T.nseg[j] = (int)so.size();
+            st.push_back(nbps);
+            so.push_back(0);
+            int *dst = nullptr, *dso = nullptr;
+            if ((rc = dev_upload(pb, &dst, st.data(), st.size()))) return rc;
+            if ((rc = dev_upload(pb, &dso, so.data(), so.size()))) return rc;
+            T.seg_start[j] = dst; T.seg_off[j] = dso;
+            for (int cl = 0; cl < T.ncoef[j]; cl++) {
+                const int c = T.iC[j] + cl;
+                const int i0 = lo[c] > 0 ? lo[c] - 1 : 0;
+                int sidx = 0;
+                while (sidx + 1 < T.nseg[j] && st[sidx + 1] <= i0) sidx++;
+                seg0[c] = sidx;
+            }
+        }
+        int *dseg0 = nullptr;
+        if ((rc = dev_upload(pb, &dseg0, seg0.data(), (size_t)T.nC))) return rc;
+        T.col_seg0 = dseg0;
     }
 
     /* Jacobian row pattern (reference src/colloc.c:243-316) */
@@ -522,6 +548,11 @@ int ntgb_create(ntgb_problem **out, const ntgb_setup *s, int device)
         if ((rc = dev_upload(pb, &dlb, pb->lowerb.data() + nlin_b, (size_t)nnl_b))) return rc;
         if ((rc = dev_upload(pb, &dub, pb->upperb.data() + nlin_b, (size_t)nnl_b))) return rc;
         T.nl_lb = dlb; T.nl_ub = dub;
+        T.nl_inline = nnl_b <= NTGB_MAXNLB;
+        for (int i = 0; i < NTGB_MAXNLB; i++) {
+            T.nl_lb_v[i] = (T.nl_inline && i < nnl_b) ? pb->lowerb[(size_t)nlin_b + i] : -DBL_MAX;
+            T.nl_ub_v[i] = (T.nl_inline && i < nnl_b) ? pb->upperb[(size_t)nlin_b + i] : DBL_MAX;
+        }
     }
 
     /* linear constraints: A (NPSOL layout, host) and band form (device) */

@@ -492,7 +492,7 @@ int launch_eval(const ntgb_launch *L)
  * library when the shared object is loaded.
  */
 #define NTGB_DEFINE_PACK(NAME, TRAITS, EXACT)                                                   \
-    static int ntgb_pack_launch_##NAME(const ntgb_launch *L) { return ntgb::launch_eval<TRAITS>(L); } \
+    static int ntgb_pack_launch_##NAME(const ntgb_launch *L) { return ntgb::launch_dispatch<TRAITS>(L); } \
     namespace {                                                                                 \
     struct ntgb_pack_registrar_##NAME {                                                         \
         ntgb_pack pk;                                                                           \

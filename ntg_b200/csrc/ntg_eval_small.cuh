@@ -1,0 +1,577 @@
+/*
+ * ntg_eval_small.cuh -- K1s: the fused evaluator for shapes whose per-
+ * breakpoint basis table fits in registers (sum_j order_j*maxderiv_j <= 64
+ * doubles and nbps <= 256: CFG-1..4, both shipped examples).
+ *
+ * Same math and same reference citations as ntg_eval_kernel.cuh (K1); what
+ * changes is the mapping, driven by ncu (profiles/r01_v1_*, r01_v2_*):
+ * K1 was limited by L1/LSU wavefronts (69 % of peak at 17 % of the HBM
+ * roofline) and instruction issue -- table and index loads repeated for every
+ * problem -- and a first persistent version spent half its time at the
+ * barrier in front of a 2-warp quadrature phase.
+ *
+ *   - persistent CTAs, one thread pinned to ONE breakpoint for the whole
+ *     launch: its slice of every output's table B_j[bp][.][.] and its offsets
+ *     are loaded once into registers; per problem it reads only the
+ *     coefficient window (staged one tile ahead into shared memory with
+ *     cp.async) and writes results -- the algorithmic traffic.
+ *   - a tile is R rounds of G problems (G = 256/nbps); phase A runs all R
+ *     rounds back to back, so that phase B -- the trapezoid quadrature of the
+ *     cost and of every gradient column, a sequential chain per column in the
+ *     reference's ascending-breakpoint order -- has ~256 independent chains
+ *     and fills the CTA instead of two warps.
+ *   - the chain rule through B is applied in phase A with the register
+ *     table; shared memory carries the band D[bp][slot], and phase B walks it
+ *     run by run (breakpoints that share a knot interval share a band
+ *     position): two shared loads and three flops per term.
+ *   - FULL = every output's order equals the pack's bound: no per-k guards.
+ */
+#ifndef NTG_EVAL_SMALL_CUH_
+#define NTG_EVAL_SMALL_CUH_
+
+#include <cstdlib>
+#include <cstring>
+
+#include "ntg_eval_kernel.cuh"
+
+namespace ntgb {
+
+template <class PK>
+__host__ __device__ constexpr int pk_tab_base(int j)
+{
+    int s = 0;
+    for (int q = 0; q < j; q++) s += PK::kMaxOrd * PK::md(q);
+    return s;
+}
+template <class PK>
+__host__ __device__ constexpr int pk_tab_doubles() { return pk_tab_base<PK>(PK::kNout); }
+
+struct SmallSmem {
+    int GR, nbps, S, nout, nC, segtot;
+    __host__ __device__ int nbpsP() const { return nbps | 1; }
+    __host__ __device__ size_t D_off() const { return 0; }                                    /* [GR][S][nbpsP] */
+    __host__ __device__ size_t f_off() const { return (size_t)GR * S * nbpsP(); }             /* [GR][nbpsP]    */
+    __host__ __device__ size_t DI_off() const { return f_off() + (size_t)GR * nbpsP(); }      /* [GR][S]        */
+    __host__ __device__ size_t DF_off() const { return DI_off() + (size_t)GR * S; }           /* [GR][S]        */
+    __host__ __device__ size_t cI_off() const { return DF_off() + (size_t)GR * S; }           /* [GR]           */
+    __host__ __device__ size_t cF_off() const { return cI_off() + GR; }                       /* [GR]           */
+    __host__ __device__ size_t viol_off() const { return cF_off() + GR; }                     /* [GR] u64       */
+    __host__ __device__ size_t dt_off() const { return viol_off() + GR; }                     /* [nbps]         */
+    __host__ __device__ size_t C_off() const { return dt_off() + nbps; }                      /* [2][GR*nC]     */
+    __host__ __device__ size_t seg_off() const { return C_off() + 2 * (size_t)GR * nC; }      /* int [2][segtot] */
+    __host__ __device__ size_t bytes() const { return seg_off() * 8 + 2 * (size_t)segtot * 4 + 8; }
+};
+
+__device__ __forceinline__ void cp_async8(double *dst_smem, const double *src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+/* band row from the register-resident table:
+ * sink(slot) gets sum_l dz[iz_j + l] * B_j[bp][k][l], l ascending from 0.0, slots in (j,k) order */
+template <class PK, bool FULL, class F>
+__device__ __forceinline__ void band_from_regs(const ntgb_devtab &T, const double *Bt, const double *dz, F &&sink)
+{
+    static_for<0, PK::kNout>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        constexpr int MD = PK::md(j);
+        constexpr int IZ = pk_iz<PK>(j);
+        constexpr int TB = pk_tab_base<PK>(j);
+        const int order = FULL ? PK::kMaxOrd : T.order[j];
+#pragma unroll
+        for (int k = 0; k < PK::kMaxOrd; k++) {
+            if (FULL || k < order) {
+                double acc = 0.0;
+#pragma unroll
+                for (int l = 0; l < MD; l++) acc = acc + dz[IZ + l] * Bt[TB + k * MD + l];
+                sink(jc, k, acc);
+            }
+        }
+    });
+}
+
+__device__ __forceinline__ double nl_bound(const ntgb_devtab &T, bool upper, int idx)
+{
+    if (T.nl_inline) return upper ? T.nl_ub_v[idx] : T.nl_lb_v[idx];
+    return __ldg((upper ? T.nl_ub : T.nl_lb) + idx);
+}
+
+/* constraint rows of one kind evaluated at this thread's breakpoint:
+ * KIND 0 initial (columns from iC_j, src/colloc.c:254), 1 trajectory, 2 final */
+template <class PK, bool FULL, int NCON, int KIND>
+__device__ __forceinline__ void emit_rows_regs(const ntgb_devtab &T, const ntgb_eval_args &A, const double *Bt,
+                                               const int *offj, int p, int bp, const double (&dfc)[NCON][pk_nz<PK>()],
+                                               int row_base)
+{
+    const int nbps = T.nbps, S = T.S;
+    if (A.jac_layout == NTGB_JAC_BAND) {
+        double *Jp = A.J + (size_t)p * T.ncnln * S + (size_t)row_base * S;
+#pragma unroll
+        for (int m = 0; m < NCON; m++) {
+            if (KIND == 1) {
+                double *ptr = Jp + (size_t)m * S * nbps + bp;
+                band_from_regs<PK, FULL>(T, Bt, dfc[m], [&](auto, int, double v) {
+                    st_stream(ptr, v);
+                    ptr += nbps;
+                });
+            } else {
+                double *ptr = Jp + (size_t)m * S;
+                band_from_regs<PK, FULL>(T, Bt, dfc[m], [&](auto, int, double v) {
+                    st_stream(ptr, v);
+                    ptr += 1;
+                });
+            }
+        }
+    } else {
+        double *Jp = A.J + (size_t)p * T.ncnln * T.nC;
+#pragma unroll
+        for (int m = 0; m < NCON; m++) {
+            const int row = (KIND == 1) ? row_base + m * nbps + bp : row_base + m;
+            band_from_regs<PK, FULL>(T, Bt, dfc[m], [&](auto jc, int k, double v) {
+                constexpr int j = decltype(jc)::value;
+                const int col = T.iC[j] + (KIND == 0 ? 0 : offj[j]) + k;
+                st_stream(Jp + (size_t)col * T.ncnln + row, v);
+            });
+        }
+    }
+}
+
+template <class PK, bool FULL>
+__global__ void __launch_bounds__(256, 2)
+ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R, int segtot)
+{
+    constexpr int NOUT = PK::kNout;
+    constexpr int NZ = pk_nz<PK>();
+    constexpr int NB = pk_tab_doubles<PK>();
+    extern __shared__ double smem[];
+    const int GR = G * R;
+    const SmallSmem L{GR, T.nbps, T.S, T.nout, T.nC, segtot};
+    const int nbps = T.nbps, nbpsP = L.nbpsP(), nC = T.nC, P = A.P, S = T.S;
+    double *D_s = smem + L.D_off();
+    double *f_s = smem + L.f_off();
+    double *DI_s = smem + L.DI_off();
+    double *DF_s = smem + L.DF_off();
+    double *cI_s = smem + L.cI_off();
+    double *cF_s = smem + L.cF_off();
+    unsigned long long *viol_s = reinterpret_cast<unsigned long long *>(smem + L.viol_off());
+    double *dt_s = smem + L.dt_off();
+    double *C_s = smem + L.C_off();
+    int *segstart_s = reinterpret_cast<int *>(smem + L.seg_off());
+    int *segoff_s = segstart_s + segtot;
+
+    const int mode_obj = A.mode_obj, mode_con = A.mode_con;
+    const bool obj_on = mode_obj >= 0 && mode_obj <= 2;
+    const bool con_on = mode_con >= 0 && mode_con <= 2 && T.ncnln > 0;
+    const bool obj_d = obj_on && mode_obj != 0, obj_v = obj_on && mode_obj != 1;
+    const bool con_d = con_on && mode_con != 0, con_v = con_on && mode_con != 1;
+    /* mode 0 gates on count==1, modes 1/2 on count!=0 (reference src/ntg.c:297-302 vs :309-314) */
+    const bool doI = PK::cb_icf != nullptr && obj_on && (mode_obj == 0 ? T.nicf == 1 : T.nicf != 0);
+    const bool doU = PK::cb_ucf != nullptr && obj_on && (mode_obj == 0 ? T.nucf == 1 : T.nucf != 0);
+    const bool doF = PK::cb_fcf != nullptr && obj_on && (mode_obj == 0 ? T.nfcf == 1 : T.nfcf != 0);
+    const bool doCI = PK::cb_nlicf != nullptr && con_on && T.nnlic != 0;
+    const bool doCT = PK::cb_nltcf != nullptr && con_on && T.nnltc != 0;
+    const bool doCF = PK::cb_nlfcf != nullptr && con_on && T.nnlfc != 0;
+    const bool wantJ = con_d && A.J != nullptr && A.jac_layout != NTGB_JAC_NONE;
+
+    /* ---- once per CTA: dt, offset runs, accumulators; once per thread: its table slice ---- */
+    for (int i = threadIdx.x; i < nbps - 1; i += blockDim.x) dt_s[i] = __ldg(T.bps + i + 1) - __ldg(T.bps + i);
+    {
+        int base = 0;
+        for (int j = 0; j < T.nout; j++) {
+            for (int i = threadIdx.x; i <= T.nseg[j]; i += blockDim.x) {
+                segstart_s[base + i] = __ldg(T.seg_start[j] + i);
+                segoff_s[base + i] = __ldg(T.seg_off[j] + i);
+            }
+            base += T.nseg[j] + 1;
+        }
+    }
+    for (int q = threadIdx.x; q < GR; q += blockDim.x) {
+        viol_s[q] = 0ull;
+        cI_s[q] = 0.0;
+        cF_s[q] = 0.0;
+    }
+
+    const int pl = threadIdx.x / nbps;
+    const int bp = threadIdx.x - pl * nbps;
+    const bool active = pl < G;
+    const int cls = (bp == 0 ? 1 : 0) | (bp == nbps - 1 ? 2 : 0);
+    double Bt[NB > 0 ? NB : 1];
+    int offj[NOUT];
+    static_for<0, NOUT>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        constexpr int MD = PK::md(j);
+        constexpr int TB = pk_tab_base<PK>(j);
+        const int order = T.order[j];
+        offj[j] = active ? __ldg(T.off[j] + bp) : 0;
+#pragma unroll
+        for (int k = 0; k < PK::kMaxOrd; k++)
+#pragma unroll
+            for (int d = 0; d < MD; d++)
+                Bt[TB + k * MD + d] = (active && k < order) ? __ldg(T.Bt[j] + (size_t)(k * MD + d) * nbps + bp) : 0.0;
+    });
+
+    const int ntiles = (P + GR - 1) / GR;
+    const int tileC = GR * nC; /* doubles of coefficients per tile (contiguous in global memory) */
+    auto stage_C = [&](int tile, int buf) {
+        const long long first = (long long)tile * tileC;
+        const long long total = (long long)P * nC;
+        for (int e = threadIdx.x; e < tileC; e += blockDim.x)
+            if (first + e < total) cp_async8(C_s + (size_t)buf * tileC + e, A.C + first + e);
+        cp_async_commit();
+    };
+    int buf = 0;
+    if ((int)blockIdx.x < ntiles) stage_C(blockIdx.x, 0);
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+        const int p0 = tile * GR;
+        cp_async_wait_all();
+        __syncthreads(); /* coefficients of this tile landed; phase B of the previous tile is done */
+        if (tile + (int)gridDim.x < ntiles) stage_C(tile + gridDim.x, buf ^ 1);
+
+        /* ---------------- phase A: this thread's breakpoint, R problems ---------------- */
+        if (active) {
+            for (int r = 0; r < R; r++) {
+                const int plr = r * G + pl;
+                const int p = p0 + plr;
+                if (p >= P) break;
+                const double *Cp = C_s + (size_t)buf * tileC + (size_t)plr * nC;
+                double z[NZ > 0 ? NZ : 1];
+                double *zp[NOUT];
+                /* Zvalue, src/colloc.c:318-326 -- k ascending from 0.0 */
+                static_for<0, NOUT>([&](auto jc) {
+                    constexpr int j = decltype(jc)::value;
+                    constexpr int MD = PK::md(j);
+                    constexpr int IZ = pk_iz<PK>(j);
+                    constexpr int TB = pk_tab_base<PK>(j);
+                    const int order = FULL ? PK::kMaxOrd : T.order[j];
+                    const double *Cw = Cp + T.iC[j] + offj[j];
+                    const unsigned mask = T.avmask[cls][j];
+                    double acc[MD];
+#pragma unroll
+                    for (int d = 0; d < MD; d++) acc[d] = 0.0;
+#pragma unroll
+                    for (int k = 0; k < PK::kMaxOrd; k++) {
+                        if (FULL || k < order) {
+                            const double ck = Cw[k];
+#pragma unroll
+                            for (int d = 0; d < MD; d++) acc[d] = acc[d] + Bt[TB + k * MD + d] * ck;
+                        }
+                    }
+#pragma unroll
+                    for (int d = 0; d < MD; d++) z[IZ + d] = ((mask >> d) & 1u) ? acc[d] : 0.0;
+                    zp[j] = &z[IZ];
+                    if (A.Z != nullptr) {
+#pragma unroll
+                        for (int d = 0; d < MD; d++)
+                            A.Z[(size_t)p * T.nZ + T.iZ[j] + (size_t)bp * MD + d] = z[IZ + d];
+                    }
+                });
+
+                double viol = 0.0;
+                int nstate = A.nstate;
+
+                /* nonlinear trajectory constraints, src/constraints.c:120-162 */
+                if constexpr (PK::cb_nltcf != nullptr && PK::kNnltc > 0) {
+                    if (doCT) {
+                        double cv[PK::kNnltc];
+                        double dfc[PK::kNnltc][NZ];
+                        double *dfp[PK::kNnltc];
+#pragma unroll
+                        for (int m = 0; m < PK::kNnltc; m++) {
+                            cv[m] = 0.0;
+                            dfp[m] = dfc[m];
+#pragma unroll
+                            for (int l = 0; l < NZ; l++) dfc[m][l] = 0.0;
+                        }
+                        int mode = mode_con, i = bp;
+                        PK::cb_nltcf(&mode, &nstate, &i, cv, dfp, zp);
+                        if (con_v) {
+                            double *cp = A.c + (size_t)p * T.ncnln + T.nnlic + bp;
+#pragma unroll
+                            for (int m = 0; m < PK::kNnltc; m++) {
+                                if (A.c != nullptr) st_stream(cp + (size_t)m * nbps, cv[m]);
+                                viol = fmax(viol, row_violation(cv[m], nl_bound(T, false, T.nnlic + m),
+                                                                nl_bound(T, true, T.nnlic + m)));
+                            }
+                        }
+                        if (wantJ) emit_rows_regs<PK, FULL, PK::kNnltc, 1>(T, A, Bt, offj, p, bp, dfc, T.nnlic);
+                    }
+                }
+                /* nonlinear initial constraints (breakpoint 0), src/constraints.c:88-117 */
+                if constexpr (PK::cb_nlicf != nullptr && PK::kNnlic > 0) {
+                    if (doCI && bp == 0) {
+                        double cv[PK::kNnlic];
+                        double dfc[PK::kNnlic][NZ];
+                        double *dfp[PK::kNnlic];
+#pragma unroll
+                        for (int m = 0; m < PK::kNnlic; m++) {
+                            cv[m] = 0.0;
+                            dfp[m] = dfc[m];
+#pragma unroll
+                            for (int l = 0; l < NZ; l++) dfc[m][l] = 0.0;
+                        }
+                        int mode = mode_con;
+                        PK::cb_nlicf(&mode, &nstate, cv, dfp, zp);
+                        if (con_v) {
+#pragma unroll
+                            for (int m = 0; m < PK::kNnlic; m++) {
+                                if (A.c != nullptr) st_stream(A.c + (size_t)p * T.ncnln + m, cv[m]);
+                                viol = fmax(viol, row_violation(cv[m], nl_bound(T, false, m), nl_bound(T, true, m)));
+                            }
+                        }
+                        if (wantJ) emit_rows_regs<PK, FULL, PK::kNnlic, 0>(T, A, Bt, offj, p, bp, dfc, 0);
+                    }
+                }
+                /* nonlinear final constraints (last breakpoint), src/constraints.c:165-195 */
+                if constexpr (PK::cb_nlfcf != nullptr && PK::kNnlfc > 0) {
+                    if (doCF && bp == nbps - 1) {
+                        double cv[PK::kNnlfc];
+                        double dfc[PK::kNnlfc][NZ];
+                        double *dfp[PK::kNnlfc];
+#pragma unroll
+                        for (int m = 0; m < PK::kNnlfc; m++) {
+                            cv[m] = 0.0;
+                            dfp[m] = dfc[m];
+#pragma unroll
+                            for (int l = 0; l < NZ; l++) dfc[m][l] = 0.0;
+                        }
+                        int mode = mode_con;
+                        const int rb = T.nnlic + T.nnltc * nbps;
+                        PK::cb_nlfcf(&mode, &nstate, cv, dfp, zp);
+                        if (con_v) {
+#pragma unroll
+                            for (int m = 0; m < PK::kNnlfc; m++) {
+                                if (A.c != nullptr) st_stream(A.c + (size_t)p * T.ncnln + rb + m, cv[m]);
+                                viol = fmax(viol, row_violation(cv[m], nl_bound(T, false, T.nnlic + T.nnltc + m),
+                                                                nl_bound(T, true, T.nnlic + T.nnltc + m)));
+                            }
+                        }
+                        if (wantJ) emit_rows_regs<PK, FULL, PK::kNnlfc, 2>(T, A, Bt, offj, p, bp, dfc, rb);
+                    }
+                }
+                if (viol > 0.0) atomicMax(&viol_s[plr], (unsigned long long)__double_as_longlong(viol));
+
+                /* unintegrated (trajectory) cost, src/cost.c:99-132: the band of dIdC (chain rule
+                 * through B) goes to shared memory for the quadrature */
+                if constexpr (PK::cb_ucf != nullptr) {
+                    if (doU) {
+                        double fv = 0.0;
+                        double df[NZ > 0 ? NZ : 1];
+#pragma unroll
+                        for (int l = 0; l < NZ; l++) df[l] = 0.0;
+                        int mode = mode_obj, i = bp;
+                        PK::cb_ucf(&mode, &nstate, &i, &fv, df, zp);
+                        f_s[plr * nbpsP + bp] = fv;
+                        if (obj_d) {
+                            double *Dp = D_s + (size_t)plr * S * nbpsP + bp;
+                            band_from_regs<PK, FULL>(T, Bt, df, [&](auto, int, double v) {
+                                *Dp = v;
+                                Dp += nbpsP;
+                            });
+                        }
+                    }
+                }
+                /* initial cost (breakpoint 0), src/cost.c:4-36 */
+                if constexpr (PK::cb_icf != nullptr) {
+                    if (doI && bp == 0) {
+                        double fv = 0.0;
+                        double df[NZ > 0 ? NZ : 1];
+#pragma unroll
+                        for (int l = 0; l < NZ; l++) df[l] = 0.0;
+                        int mode = mode_obj;
+                        PK::cb_icf(&mode, &nstate, &fv, df, zp);
+                        cI_s[plr] = fv;
+                        if (obj_d) {
+                            double *Dp = DI_s + plr * S;
+                            band_from_regs<PK, FULL>(T, Bt, df, [&](auto, int, double v) { *Dp++ = v; });
+                        }
+                    }
+                }
+                /* final cost (last breakpoint), src/cost.c:141-174 */
+                if constexpr (PK::cb_fcf != nullptr) {
+                    if (doF && bp == nbps - 1) {
+                        double fv = 0.0;
+                        double df[NZ > 0 ? NZ : 1];
+#pragma unroll
+                        for (int l = 0; l < NZ; l++) df[l] = 0.0;
+                        int mode = mode_obj;
+                        PK::cb_fcf(&mode, &nstate, &fv, df, zp);
+                        cF_s[plr] = fv;
+                        if (obj_d) {
+                            double *Dp = DF_s + plr * S;
+                            band_from_regs<PK, FULL>(T, Bt, df, [&](auto, int, double v) { *Dp++ = v; });
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        /* ------- phase B: one chain per (problem, column); the scalar cost is one more column ------- */
+        const int items = GR * (nC + 1);
+        for (int q = threadIdx.x; q < items; q += blockDim.x) {
+            const int plr = q / (nC + 1);
+            const int c = q - plr * (nC + 1);
+            const int pb = p0 + plr;
+            if (pb >= P) continue;
+            if (c == nC) {
+                /* IntegrateVector TRAPEZOID, src/integrator.c:21-24; y = I + In + F, src/ntg.c:303,328 */
+                double In = 0.0;
+                if (doU && obj_v) {
+                    const double *fp = f_s + plr * nbpsP;
+                    double fprev = fp[0];
+#pragma unroll 4
+                    for (int i = 0; i < nbps - 1; i++) {
+                        const double fn = fp[i + 1];
+                        In = In + (dt_s[i] * (fn + fprev)) / 2;
+                        fprev = fn;
+                    }
+                }
+                const double y = (cI_s[plr] + In) + cF_s[plr];
+                if (obj_v && A.f != nullptr) A.f[pb] = y;
+                if (A.result != nullptr) {
+                    A.result[2 * (size_t)pb] = obj_v ? y : 0.0;
+                    A.result[2 * (size_t)pb + 1] = __longlong_as_double((long long)viol_s[plr]);
+                }
+                viol_s[plr] = 0ull; /* ready for the next tile */
+                continue;
+            }
+            if (!obj_d || A.g == nullptr) continue;
+            /* IntegrateFMatrixCols TRAPEZOID over the band (src/integrator.c:44-48 on the matrix of
+             * src/cost.c:118-132), ascending breakpoint; then Vector3Add, src/ntg.c:329 */
+            double gI = 0.0, gU = 0.0, gF = 0.0;
+            int segbase = 0;
+            static_for<0, NOUT>([&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                const int sb = segbase;
+                segbase += T.nseg[j] + 1;
+                const int cl = c - T.iC[j];
+                if (cl < 0 || cl >= T.ncoef[j]) return;
+                const unsigned order = FULL ? PK::kMaxOrd : T.order[j];
+                const int *ss = segstart_s + sb;
+                const int *so = segoff_s + sb;
+                const double *Dj = D_s + ((size_t)plr * S + T.jk0[j]) * nbpsP;
+                if (doU) {
+                    const int lo = __ldg(T.col_lo + c), hi = __ldg(T.col_hi + c);
+                    const int i0 = lo > 0 ? lo - 1 : 0;
+                    const int nend = (hi < nbps - 2 ? hi : nbps - 2) + 1;
+                    if (i0 < nend) {
+                        int s = __ldg(T.col_seg0 + c);
+                        int k = cl - so[s];
+                        double dcur = ((unsigned)k < order) ? Dj[k * nbpsP + i0] : 0.0;
+                        int n = i0 + 1;
+                        while (n <= nend) {
+                            int snext = ss[s + 1];
+                            if (n >= snext) {
+                                s++;
+                                k = cl - so[s];
+                                snext = ss[s + 1];
+                            }
+                            const int segend = snext - 1 < nend ? snext - 1 : nend;
+                            if ((unsigned)k < order) {
+                                const double *ptr = Dj + k * nbpsP;
+#pragma unroll 4
+                                for (; n <= segend; n++) {
+                                    const double dn = ptr[n];
+                                    gU = gU + (dt_s[n - 1] * (dn + dcur)) / 2;
+                                    dcur = dn;
+                                }
+                            } else { /* leaving the band: one term against an exact zero, the rest are zeros */
+                                gU = gU + (dt_s[n - 1] * (0.0 + dcur)) / 2;
+                                dcur = 0.0;
+                                n = segend + 1;
+                            }
+                        }
+                    }
+                }
+                if (doI && (unsigned)cl < order) gI = DI_s[plr * S + T.jk0[j] + cl]; /* offset 0, src/colloc.c:254 */
+                if (doF) {
+                    const int k = cl - so[T.nseg[j] - 1];
+                    if ((unsigned)k < order) gF = DF_s[plr * S + T.jk0[j] + k];
+                }
+            });
+            st_stream(A.g + (size_t)pb * nC + c, (gI + gU) + gF);
+        }
+        /* the barrier at the top of the next iteration separates this phase B from the next phase A */
+    }
+    cp_async_wait_all();
+}
+
+/* does this problem fit the register-table kernel? */
+template <class PK>
+__host__ inline bool small_shape_ok(const ntgb_devtab &T)
+{
+    return pk_tab_doubles<PK>() <= 64 && T.nbps <= 256;
+}
+
+template <class PK>
+int launch_eval_small(const ntgb_launch *L)
+{
+    const ntgb_devtab &T = L->tab;
+    const int nbps = T.nbps, P = L->args.P;
+    int block = 256;
+    int G = block / nbps;
+    if (G > P) {
+        G = P > 0 ? P : 1;
+        int need = ((G * nbps) + 31) / 32 * 32;
+        if (need < 64) need = 64;
+        if (need < block) block = need;
+    }
+    int segtot = 0;
+    bool full = true;
+    for (int j = 0; j < T.nout; j++) {
+        segtot += T.nseg[j] + 1;
+        full = full && T.order[j] == PK::kMaxOrd;
+    }
+    /* R rounds per tile: enough (problem, column) chains to fill the CTA in phase B; for small
+     * batches, enough problems per tile that the whole batch is ONE wave of resident CTAs (a
+     * second, mostly empty wave would double the latency); within ~100 KB of shared memory. */
+    const int slots = 2 * L->sm_count; /* __launch_bounds__(256, 2) */
+    int R = (block + G * (T.nC + 1) - 1) / (G * (T.nC + 1));
+    const int r_wave = (int)(((long long)P + (long long)G * slots - 1) / ((long long)G * slots));
+    if (r_wave <= 8) R = r_wave;   /* single wave */
+    if (R < 1) R = 1;
+    if (R > 8) R = 8;
+    while (R > 1 && SmallSmem{G * R, nbps, T.S, T.nout, T.nC, segtot}.bytes() > 100 * 1024) R--;
+    SmallSmem lay{G * R, nbps, T.S, T.nout, T.nC, segtot};
+    const size_t smem = lay.bytes();
+    if (smem > (size_t)L->max_smem_optin) return -1001;
+    auto kern = full ? ntg_eval_small_kernel<PK, true> : ntg_eval_small_kernel<PK, false>;
+    cudaError_t e;
+    if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    int nb = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, block, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (nb < 1) nb = 1;
+    const int ntiles = (P + G * R - 1) / (G * R);
+    int grid = nb * L->sm_count;
+    if (grid > ntiles) grid = ntiles;
+    if (grid < 1) return 0;
+    kern<<<grid, block, smem, (cudaStream_t)L->args.stream>>>(T, L->args, G, R, segtot);
+    return (int)cudaGetLastError();
+}
+
+/* dispatcher used by NTGB_DEFINE_PACK */
+template <class PK>
+int launch_dispatch(const ntgb_launch *L)
+{
+    /* NTG_B200_KERNEL=general forces K1 (A/B measurements, tests of both kernels) */
+    const char *env = getenv("NTG_B200_KERNEL");
+    const bool force_general = env != nullptr && strcmp(env, "general") == 0;
+    if constexpr (pk_tab_doubles<PK>() <= 64) {
+        if (!force_general && small_shape_ok<PK>(L->tab)) {
+            const int rc = launch_eval_small<PK>(L);
+            if (rc != -1001) return rc;
+        }
+    }
+    return launch_eval<PK>(L);
+}
+
+} /* namespace ntgb */
+#endif

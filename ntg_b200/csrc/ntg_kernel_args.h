@@ -9,9 +9,10 @@
 
 #include "ntg_b200.h"
 
-#define NTGB_KERNEL_ABI 3
+#define NTGB_KERNEL_ABI 4
 #define NTGB_MAXOUT 8      /* outputs per problem the device tables can describe */
 #define NTGB_MAXORDER 20   /* PGS bsplvb work arrays: jmax = 20   */
+#define NTGB_MAXNLB 16     /* nonlinear bounds carried by value in the kernel params */
 
 /* Device-resident, batch-shared problem description (built once by K0). */
 typedef struct ntgb_devtab {
@@ -29,6 +30,15 @@ typedef struct ntgb_devtab {
     const double *bps;              /* [nbps]                                              */
     const double *nl_lb, *nl_ub;    /* [nnlic+nnltc+nnlfc] compact nonlinear bounds        */
     const int *col_lo, *col_hi;     /* [nC] first/last breakpoint whose band holds column  */
+    /* runs of consecutive breakpoints with equal block offset, per output:
+     * seg_start[j][s] .. seg_start[j][s+1]-1 share seg_off[j][s]; seg_start[j][nseg] = nbps */
+    int nseg[NTGB_MAXOUT];
+    const int *seg_start[NTGB_MAXOUT];
+    const int *seg_off[NTGB_MAXOUT];
+    const int *col_seg0;            /* [nC] run that holds breakpoint max(col_lo-1, 0)       */
+    /* the same compact nonlinear bounds by value (constant bank), when they fit */
+    int nl_inline;
+    double nl_lb_v[NTGB_MAXNLB], nl_ub_v[NTGB_MAXNLB];
 } ntgb_devtab;
 
 typedef struct ntgb_launch {

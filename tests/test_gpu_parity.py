@@ -134,6 +134,20 @@ def test_modes(torch_cuda, port, mode):
     pb.close()
 
 
+@pytest.mark.parametrize("name", ["cfg2_vanderpol", "cfg4_kincar64", "endpoint"])
+def test_general_kernel_on_small_shapes(torch_cuda, port, name, monkeypatch):
+    """Small shapes normally take the register-table kernel K1s; NTG_B200_KERNEL=general
+    forces the general kernel K1 so both are held to the same bar on the same inputs."""
+    monkeypatch.setenv("NTG_B200_KERNEL", "general")
+    spec, X = golden_spec(name)
+    o = port.eval(spec, X, dense=False)
+    pb, r = gpu_eval(torch_cuda, spec, X, False)
+    cmp = assert_bitexact if name in NO_LIBM else assert_close
+    for k in ("f", "g", "c", "Jband"):
+        cmp(r[k], o[k], f"{name}.{k} (general kernel)")
+    pb.close()
+
+
 @pytest.mark.parametrize("P", [1, 2, 3, 11, 12, 13, 255, 257, 1000])
 def test_ragged_batches(torch_cuda, port, P):
     """batch sizes around the tile size G (12 problems per CTA at nbps = 20), incl. P = 1"""

@@ -48,10 +48,13 @@ __host__ __device__ constexpr int pk_tab_doubles() { return pk_tab_base<PK>(PK::
 
 struct SmallSmem {
     int GR, nbps, S, nout, nC, segtot;
-    __host__ __device__ int nbpsP() const { return nbps | 1; }
-    __host__ __device__ size_t D_off() const { return 0; }                                    /* [GR][S][nbpsP] */
-    __host__ __device__ size_t f_off() const { return (size_t)GR * S * nbpsP(); }             /* [GR][nbpsP]    */
-    __host__ __device__ size_t DI_off() const { return f_off() + (size_t)GR * nbpsP(); }      /* [GR][S]        */
+    /* problem index is the FASTEST dimension of D and f (odd pitch GRP): phase A lanes are
+     * consecutive breakpoints (stride GRP doubles, conflict-free because GRP is odd), phase B
+     * lanes are consecutive problems of one column (stride 1) */
+    __host__ __device__ int GRP() const { return GR | 1; }
+    __host__ __device__ size_t D_off() const { return 0; }                                    /* [S][nbps][GRP] */
+    __host__ __device__ size_t f_off() const { return (size_t)S * nbps * GRP(); }             /* [nbps][GRP]    */
+    __host__ __device__ size_t DI_off() const { return f_off() + (size_t)nbps * GRP(); }      /* [GR][S]        */
     __host__ __device__ size_t DF_off() const { return DI_off() + (size_t)GR * S; }           /* [GR][S]        */
     __host__ __device__ size_t cI_off() const { return DF_off() + (size_t)GR * S; }           /* [GR]           */
     __host__ __device__ size_t cF_off() const { return cI_off() + GR; }                       /* [GR]           */
@@ -149,7 +152,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
     extern __shared__ double smem[];
     const int GR = G * R;
     const SmallSmem L{GR, T.nbps, T.S, T.nout, T.nC, segtot};
-    const int nbps = T.nbps, nbpsP = L.nbpsP(), nC = T.nC, P = A.P, S = T.S;
+    const int nbps = T.nbps, GRP = L.GRP(), nC = T.nC, P = A.P, S = T.S;
     double *D_s = smem + L.D_off();
     double *f_s = smem + L.f_off();
     double *DI_s = smem + L.DI_off();
@@ -364,12 +367,13 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                         for (int l = 0; l < NZ; l++) df[l] = 0.0;
                         int mode = mode_obj, i = bp;
                         PK::cb_ucf(&mode, &nstate, &i, &fv, df, zp);
-                        f_s[plr * nbpsP + bp] = fv;
+                        f_s[bp * GRP + plr] = fv;
                         if (obj_d) {
-                            double *Dp = D_s + (size_t)plr * S * nbpsP + bp;
+                            double *Dp = D_s + (size_t)bp * GRP + plr;
+                            const int pitch = nbps * GRP;
                             band_from_regs<PK, FULL>(T, Bt, df, [&](auto, int, double v) {
                                 *Dp = v;
-                                Dp += nbpsP;
+                                Dp += pitch;
                             });
                         }
                     }
@@ -413,19 +417,19 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
         /* ------- phase B: one chain per (problem, column); the scalar cost is one more column ------- */
         const int items = GR * (nC + 1);
         for (int q = threadIdx.x; q < items; q += blockDim.x) {
-            const int plr = q / (nC + 1);
-            const int c = q - plr * (nC + 1);
+            const int c = q / GR; /* column-major: a warp holds whole columns, its lanes walk the same runs */
+            const int plr = q - c * GR;
             const int pb = p0 + plr;
             if (pb >= P) continue;
             if (c == nC) {
                 /* IntegrateVector TRAPEZOID, src/integrator.c:21-24; y = I + In + F, src/ntg.c:303,328 */
                 double In = 0.0;
                 if (doU && obj_v) {
-                    const double *fp = f_s + plr * nbpsP;
+                    const double *fp = f_s + plr;
                     double fprev = fp[0];
 #pragma unroll 4
                     for (int i = 0; i < nbps - 1; i++) {
-                        const double fn = fp[i + 1];
+                        const double fn = fp[(i + 1) * GRP];
                         In = In + (dt_s[i] * (fn + fprev)) / 2;
                         fprev = fn;
                     }
@@ -453,7 +457,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                 const unsigned order = FULL ? PK::kMaxOrd : T.order[j];
                 const int *ss = segstart_s + sb;
                 const int *so = segoff_s + sb;
-                const double *Dj = D_s + ((size_t)plr * S + T.jk0[j]) * nbpsP;
+                const double *Dj = D_s + (size_t)T.jk0[j] * nbps * GRP + plr;
                 if (doU) {
                     const int lo = __ldg(T.col_lo + c), hi = __ldg(T.col_hi + c);
                     const int i0 = lo > 0 ? lo - 1 : 0;
@@ -461,7 +465,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                     if (i0 < nend) {
                         int s = __ldg(T.col_seg0 + c);
                         int k = cl - so[s];
-                        double dcur = ((unsigned)k < order) ? Dj[k * nbpsP + i0] : 0.0;
+                        double dcur = ((unsigned)k < order) ? Dj[(k * nbps + i0) * GRP] : 0.0;
                         int n = i0 + 1;
                         while (n <= nend) {
                             int snext = ss[s + 1];
@@ -472,10 +476,10 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                             }
                             const int segend = snext - 1 < nend ? snext - 1 : nend;
                             if ((unsigned)k < order) {
-                                const double *ptr = Dj + k * nbpsP;
+                                const double *ptr = Dj + (size_t)(k * nbps + n) * GRP;
 #pragma unroll 4
-                                for (; n <= segend; n++) {
-                                    const double dn = ptr[n];
+                                for (; n <= segend; n++, ptr += GRP) {
+                                    const double dn = *ptr;
                                     gU = gU + (dt_s[n - 1] * (dn + dcur)) / 2;
                                     dcur = dn;
                                 }

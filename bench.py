@@ -245,17 +245,43 @@ def time_workload(torch, pb, spec, cfg, P, steps, warmup, dist=None, world=1, us
                 pb.launch(cap)
             graphs.append(g)
 
-    def step(i):
+    # N > 1: the 16 B/problem result gather of step i runs on NCCL's stream while the kernel of
+    # step i+1 runs (async_op); two result tables alternate so the gather never reads a table
+    # the next kernel is writing.
+    res2 = [torch.empty((P, 2), dtype=torch.float64, device=dev) for _ in range(2)] if dist else None
+    gath2 = [torch.empty((world * P, 2), dtype=torch.float64, device=dev) for _ in range(2)] if dist else None
+    if dist is not None:
+        args2 = [[pb.eval_args(x, dict(o, result=res2[b]), 2, 2, JAC_BAND, 0, stream.cuda_stream) for x, o in sets]
+                 for b in range(2)]
+    pending = [None, None]
+
+    def step(i, ev=None):
         s = i % nset
-        if graphs is not None:
+        if ev is not None:
+            ev[0].record()
+        if dist is not None:
+            b = i % 2
+            if pending[b] is not None:
+                pending[b].wait()          # the gather that last read res2[b] is done
+            pb.launch(args2[b][s])
+        elif graphs is not None:
             graphs[s].replay()
         else:
             pb.launch(args[s])
+        if ev is not None:
+            ev[1].record()
         if dist is not None:
-            dist.all_gather_into_tensor(gathered[s], sets[s][1]["result"])
+            pending[i % 2] = dist.all_gather_into_tensor(gath2[i % 2], res2[i % 2], async_op=True)
+
+    def drain():
+        for b in range(2):
+            if pending[b] is not None:
+                pending[b].wait()
+                pending[b] = None
 
     for i in range(warmup):
         step(i)
+    drain()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if dist is not None:
@@ -263,22 +289,19 @@ def time_workload(torch, pb, spec, cfg, P, steps, warmup, dist=None, world=1, us
     torch.cuda.synchronize(dev)
     e0.record()
     for i in range(steps):
-        s = i % nset
-        ev[i][0].record()
-        if graphs is not None:
-            graphs[s].replay()
-        else:
-            pb.launch(args[s])
-        ev[i][1].record()
-        if dist is not None:
-            dist.all_gather_into_tensor(gathered[s], sets[s][1]["result"])
+        step(i, ev[i])
+    drain()
     e1.record()
     torch.cuda.synchronize(dev)
     if dist is not None:
         dist.barrier()
+        want = torch.cat([res2[(steps - 1) % 2]] * 1)
+        got = gath2[(steps - 1) % 2]
+        r0 = dist.get_rank()
+        assert torch.equal(got[r0 * P:(r0 + 1) * P], want), "gathered table does not hold this rank's rows"
     total_ms = e0.elapsed_time(e1)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
-    chk = float(sets[0][1]["result"][:, 0].sum().item())
+    chk = float((res2[0] if dist is not None else sets[0][1]["result"])[:, 0].sum().item())
     assert np.isfinite(chk), "non-finite objective in the timed run"
     return {"ms_per_step": total_ms / steps, "kernel_ms": kernel_ms, "launches": steps, "nset": nset,
             "footprint_mb": per_set * nset / 1e6}

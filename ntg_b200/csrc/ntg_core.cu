@@ -292,7 +292,7 @@ void host_band_row(const ntgb_problem *pb, const double *dz, int bp, double *ban
 extern "C" {
 
 const char *ntgb_last_error(void) { return g_err.c_str(); }
-const char *ntgb_version(void) { return "ntg_b200 0.1 (sm_100a, kernel ABI 4)"; }
+const char *ntgb_version(void) { return "ntg_b200 0.1 (sm_100a, kernel ABI 5)"; }
 
 int ntgb_register_pack(const ntgb_pack *pack)
 {
@@ -520,6 +520,56 @@ int ntgb_create(ntgb_problem **out, const ntgb_setup *s, int device)
         int *dseg0 = nullptr;
         if ((rc = dev_upload(pb, &dseg0, seg0.data(), (size_t)T.nC))) return rc;
         T.col_seg0 = dseg0;
+    }
+
+    /* do all outputs share one spline setup (one table serves all)? */
+    T.one_table = 1;
+    for (int j = 1; j < nout; j++)
+        if (T.order[j] != T.order[0] || T.mult[j] != T.mult[0] || T.maxderiv[j] != T.maxderiv[0] ||
+            pb->ninterv[j] != pb->ninterv[0] || pb->knots[j] != pb->knots[0])
+            T.one_table = 0;
+
+    /* quadrature plan for the cluster kernel (long horizons, one shared table) */
+    T.plan_ptr = nullptr; T.plan = nullptr; T.plan_cl = 0; T.plan_bpc = 0; T.plan_cwin = 0;
+    if (T.one_table && nbps > 256 && nbps <= 8 * 224) {
+        int CL, bpc;
+        ntgb_cluster_geometry(nbps, &CL, &bpc);
+        std::vector<int> ptr(T.ncoef[0] + 1, 0);
+        std::vector<int2> ent;
+        for (int cl = 0; cl < T.ncoef[0]; cl++) {
+            int lo = nbps, hi = -1;
+            for (int bp = 0; bp < nbps; bp++) {
+                const int k = cl - pb->hoff[bp];
+                if (k >= 0 && k < T.order[0]) { if (bp < lo) lo = bp; if (bp > hi) hi = bp; }
+            }
+            ptr[cl] = (int)ent.size();
+            if (hi >= 0) {
+                const int i0 = lo > 0 ? lo - 1 : 0;
+                const int nend = (hi < nbps - 2 ? hi : nbps - 2) + 1;
+                for (int n = i0; n <= nend; n++) {
+                    const int k = cl - pb->hoff[n];
+                    const int r = n / bpc, li = n - r * bpc;
+                    const int o24 = (k >= 0 && k < T.order[0]) ? k * bpc + li : 0xffffff;
+                    ent.push_back(make_int2(n, (r << 24) | o24));
+                }
+            }
+        }
+        ptr[T.ncoef[0]] = (int)ent.size();
+        if (ent.empty()) ent.push_back(make_int2(0, 0));
+        int *dptr = nullptr; int2 *dent = nullptr;
+        if ((rc = dev_upload(pb, &dptr, ptr.data(), ptr.size()))) return rc;
+        if ((rc = dev_upload(pb, &dent, ent.data(), ent.size()))) return rc;
+        T.plan_ptr = dptr; T.plan = dent; T.plan_cl = CL; T.plan_bpc = bpc;
+        int wmax = 0;
+        for (int r = 0; r < CL; r++) {
+            int lo = 0x7fffffff, hi = -1;
+            for (int bp = r * bpc; bp < (r + 1) * bpc && bp < nbps; bp++) {
+                lo = pb->hoff[bp] < lo ? pb->hoff[bp] : lo;
+                hi = pb->hoff[bp] > hi ? pb->hoff[bp] : hi;
+            }
+            if (hi >= 0 && hi + T.order[0] - lo > wmax) wmax = hi + T.order[0] - lo;
+        }
+        T.plan_cwin = wmax * nout;
     }
 
     /* Jacobian row pattern (reference src/colloc.c:243-316) */

@@ -75,14 +75,14 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 /* band row from the register-resident table:
  * sink(slot) gets sum_l dz[iz_j + l] * B_j[bp][k][l], l ascending from 0.0, slots in (j,k) order */
-template <class PK, bool FULL, class F>
+template <class PK, bool FULL, bool ONE = false, class F>
 __device__ __forceinline__ void band_from_regs(const ntgb_devtab &T, const double *Bt, const double *dz, F &&sink)
 {
     static_for<0, PK::kNout>([&](auto jc) {
         constexpr int j = decltype(jc)::value;
         constexpr int MD = PK::md(j);
         constexpr int IZ = pk_iz<PK>(j);
-        constexpr int TB = pk_tab_base<PK>(j);
+        constexpr int TB = ONE ? 0 : pk_tab_base<PK>(j); /* ONE: every output shares table 0 */
         const int order = FULL ? PK::kMaxOrd : T.order[j];
 #pragma unroll
         for (int k = 0; k < PK::kMaxOrd; k++) {
@@ -104,7 +104,7 @@ __device__ __forceinline__ double nl_bound(const ntgb_devtab &T, bool upper, int
 
 /* constraint rows of one kind evaluated at this thread's breakpoint:
  * KIND 0 initial (columns from iC_j, src/colloc.c:254), 1 trajectory, 2 final */
-template <class PK, bool FULL, int NCON, int KIND>
+template <class PK, bool FULL, int NCON, int KIND, bool ONE = false>
 __device__ __forceinline__ void emit_rows_regs(const ntgb_devtab &T, const ntgb_eval_args &A, const double *Bt,
                                                const int *offj, int p, int bp, const double (&dfc)[NCON][pk_nz<PK>()],
                                                int row_base)
@@ -116,13 +116,13 @@ __device__ __forceinline__ void emit_rows_regs(const ntgb_devtab &T, const ntgb_
         for (int m = 0; m < NCON; m++) {
             if (KIND == 1) {
                 double *ptr = Jp + (size_t)m * S * nbps + bp;
-                band_from_regs<PK, FULL>(T, Bt, dfc[m], [&](auto, int, double v) {
+                band_from_regs<PK, FULL, ONE>(T, Bt, dfc[m], [&](auto, int, double v) {
                     st_stream(ptr, v);
                     ptr += nbps;
                 });
             } else {
                 double *ptr = Jp + (size_t)m * S;
-                band_from_regs<PK, FULL>(T, Bt, dfc[m], [&](auto, int, double v) {
+                band_from_regs<PK, FULL, ONE>(T, Bt, dfc[m], [&](auto, int, double v) {
                     st_stream(ptr, v);
                     ptr += 1;
                 });
@@ -133,7 +133,7 @@ __device__ __forceinline__ void emit_rows_regs(const ntgb_devtab &T, const ntgb_
 #pragma unroll
         for (int m = 0; m < NCON; m++) {
             const int row = (KIND == 1) ? row_base + m * nbps + bp : row_base + m;
-            band_from_regs<PK, FULL>(T, Bt, dfc[m], [&](auto jc, int k, double v) {
+            band_from_regs<PK, FULL, ONE>(T, Bt, dfc[m], [&](auto jc, int k, double v) {
                 constexpr int j = decltype(jc)::value;
                 const int col = T.iC[j] + (KIND == 0 ? 0 : offj[j]) + k;
                 st_stream(Jp + (size_t)col * T.ncnln + row, v);
@@ -559,22 +559,6 @@ int launch_eval_small(const ntgb_launch *L)
     if (grid < 1) return 0;
     kern<<<grid, block, smem, (cudaStream_t)L->args.stream>>>(T, L->args, G, R, segtot);
     return (int)cudaGetLastError();
-}
-
-/* dispatcher used by NTGB_DEFINE_PACK */
-template <class PK>
-int launch_dispatch(const ntgb_launch *L)
-{
-    /* NTG_B200_KERNEL=general forces K1 (A/B measurements, tests of both kernels) */
-    const char *env = getenv("NTG_B200_KERNEL");
-    const bool force_general = env != nullptr && strcmp(env, "general") == 0;
-    if constexpr (pk_tab_doubles<PK>() <= 64) {
-        if (!force_general && small_shape_ok<PK>(L->tab)) {
-            const int rc = launch_eval_small<PK>(L);
-            if (rc != -1001) return rc;
-        }
-    }
-    return launch_eval<PK>(L);
 }
 
 } /* namespace ntgb */

@@ -9,7 +9,9 @@
 
 #include "ntg_b200.h"
 
-#define NTGB_KERNEL_ABI 4
+#include <vector_types.h>
+
+#define NTGB_KERNEL_ABI 6
 #define NTGB_MAXOUT 8      /* outputs per problem the device tables can describe */
 #define NTGB_MAXORDER 20   /* PGS bsplvb work arrays: jmax = 20   */
 #define NTGB_MAXNLB 16     /* nonlinear bounds carried by value in the kernel params */
@@ -38,8 +40,28 @@ typedef struct ntgb_devtab {
     const int *col_seg0;            /* [nC] run that holds breakpoint max(col_lo-1, 0)       */
     /* the same compact nonlinear bounds by value (constant bank), when they fit */
     int nl_inline;
+    int one_table;                  /* every output has the same knots/order/mult/maxderiv   */
+    /* quadrature plan of the cluster kernel (one_table only): for local column cl of an output,
+     * entries plan[plan_ptr[cl] .. plan_ptr[cl+1]) list the breakpoints of its trapezoid chain in
+     * ascending order: .x = breakpoint n, .y = (cluster rank that owns n << 24) | o24 with
+     * o24 = k * bpc + (n - rank * bpc), the position of (band slot k, breakpoint n) inside one
+     * output's block of that CTA's D array, or 0xffffff outside the band.  The first entry only
+     * seeds the chain. */
+    const int *plan_ptr;
+    const int2 *plan;
+    int plan_cl, plan_bpc;          /* cluster geometry the plan was built for               */
+    int plan_cwin;                  /* doubles of coefficients the widest CTA stages per problem */
     double nl_lb_v[NTGB_MAXNLB], nl_ub_v[NTGB_MAXNLB];
 } ntgb_devtab;
+
+/* cluster geometry of K1c for a horizon of nbps breakpoints (shared by core and launcher) */
+static inline void ntgb_cluster_geometry(int nbps, int *CL, int *bpc)
+{
+    /* at most 224 breakpoints per CTA: 7 warps pinned to breakpoints + 1 service warp = 256 threads */
+    int cl = nbps <= 2 * 224 ? 2 : (nbps <= 4 * 224 ? 4 : 8);
+    *CL = cl;
+    *bpc = (nbps + cl - 1) / cl;
+}
 
 typedef struct ntgb_launch {
     int abi;

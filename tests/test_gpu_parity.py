@@ -148,6 +148,45 @@ def test_general_kernel_on_small_shapes(torch_cuda, port, name, monkeypatch):
     pb.close()
 
 
+@pytest.mark.parametrize("ninterv,P", [(200, 3), (150, 75), (300, 5), (640, 2)])
+@pytest.mark.parametrize("fast", [False, True], ids=["exact", "fast"])
+def test_cluster_kernel_long_horizons(torch_cuda, port, ninterv, P, fast):
+    """K1c (thread-block clusters of 2/4/8 CTAs, DSMEM halo) on long horizons: nbps = 401 / 301 /
+    601 / 1281, batch sizes below, at and above the number of clusters; all modes' outputs."""
+    spec = configs.syn6(ninterv, name=f"syn6_{ninterv}")
+    X = configs.coefficients("cfg5", P, spec, seed=ninterv)
+    o = port.eval(spec, X, dense=False, band=True)
+    pb, r = gpu_eval(torch_cuda, spec, X, fast, want_Z=True)
+    cmp = assert_bitexact if not fast else assert_close
+    for k in ("f", "g", "c", "Jband"):
+        cmp(r[k], o[k], f"syn6/{ninterv}.{k}")
+    assert_close(r["result"][:, 1], violation(spec, o["c"]), "violation")
+    av = [(j, d) for j in range(6) for d in range(4)]
+    cmp(r["Z"][0], port.updateZ(spec, X[0], av, 1), "flat outputs")
+    pb.close()
+    if ninterv == 150 and not fast:   # values-only and derivatives-only modes through the cluster kernel
+        for mode in (0, 1):
+            pb, r = gpu_eval(torch_cuda, spec, X, fast, mode_obj=mode, mode_con=mode)
+            if mode == 0:
+                assert_bitexact(r["f"], o["f"], "f"); assert_bitexact(r["c"], o["c"], "c")
+                assert np.all(r["g"] == 0) and np.all(r["J"] == 0)
+            else:
+                assert_bitexact(r["g"], o["g"], "g"); assert_bitexact(r["Jband"], o["Jband"], "J")
+                assert np.all(r["f"] == 0) and np.all(r["c"] == 0)
+            pb.close()
+
+
+def test_cluster_kernel_dense_layout(torch_cuda, port):
+    spec = configs.syn6(140, name="syn6_140")
+    X = configs.coefficients("cfg5", 2, spec, seed=3)
+    o = port.eval(spec, X, dense=True, band=False)
+    pb, r = gpu_eval(torch_cuda, spec, X, False, jac=JAC_DENSE)
+    written = ~np.isnan(o["Jdense"])
+    assert np.all(r["J"][~written] == 0.0)
+    assert_bitexact(r["J"][written], o["Jdense"][written], "dense Jacobian through K1c")
+    pb.close()
+
+
 @pytest.mark.parametrize("P", [1, 2, 3, 11, 12, 13, 255, 257, 1000])
 def test_ragged_batches(torch_cuda, port, P):
     """batch sizes around the tile size G (12 problems per CTA at nbps = 20), incl. P = 1"""

@@ -10,6 +10,8 @@ ap.add_argument("--variants", default="exact,fast")
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--p5", type=int, default=4096)
 ap.add_argument("--dense", action="store_true")
+ap.add_argument("--mode_obj", type=int, default=2)
+ap.add_argument("--mode_con", type=int, default=2)
 a = ap.parse_args()
 HBM = 6529.1
 L2 = 126e6
@@ -25,7 +27,7 @@ for cfg in a.cfgs.split(","):
         nset = max(1, int(np.ceil(2 * L2 / per_set))) if per_set < 2 * L2 else 1
         nset = min(nset, 64)
         sets = [(X.clone(), pb.alloc_outputs(P, jac)) for _ in range(nset)]
-        args = [pb.eval_args(x, o, 2, 2, jac, 0, torch.cuda.current_stream().cuda_stream) for x, o in sets]
+        args = [pb.eval_args(x, o, a.mode_obj, a.mode_con, jac, 0, torch.cuda.current_stream().cuda_stream) for x, o in sets]
         for i in range(3): pb.launch(args[i % nset])
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

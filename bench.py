@@ -38,6 +38,8 @@ sys.path.insert(0, ROOT)
 from ntg_b200 import JAC_BAND, configs  # noqa: E402
 
 L2_BYTES = 126e6
+KERNEL_OF = {"cfg2": "ntgb::ntg_eval_small_kernel<vdp> (K1s)", "cfg3": "ntgb::ntg_eval_small_kernel<kincar> (K1s)",
+             "cfg4": "ntgb::ntg_eval_small_kernel<kincar> (K1s)", "cfg5": "ntgb::ntg_eval_cluster_kernel<syn6> (K1c)"}
 METRIC = "collocation_evals_per_sec"
 UNIT = "evals/s"
 
@@ -248,19 +250,21 @@ def time_workload(torch, pb, spec, cfg, P, steps, warmup, dist=None, world=1, us
     # N > 1: the 16 B/problem result gather of step i runs on NCCL's stream while the kernel of
     # step i+1 runs (async_op); two result tables alternate so the gather never reads a table
     # the next kernel is writing.
-    res2 = [torch.empty((P, 2), dtype=torch.float64, device=dev) for _ in range(2)] if dist else None
-    gath2 = [torch.empty((world * P, 2), dtype=torch.float64, device=dev) for _ in range(2)] if dist else None
+    NB = 4  # the gather of step i runs after kernel i+1 has drained (persistent CTAs fill every SM),
+    #         i.e. during kernel i+2; with 4 tables kernel i+4 never waits for it
+    res2 = [torch.empty((P, 2), dtype=torch.float64, device=dev) for _ in range(NB)] if dist else None
+    gath2 = [torch.empty((world * P, 2), dtype=torch.float64, device=dev) for _ in range(NB)] if dist else None
     if dist is not None:
         args2 = [[pb.eval_args(x, dict(o, result=res2[b]), 2, 2, JAC_BAND, 0, stream.cuda_stream) for x, o in sets]
-                 for b in range(2)]
-    pending = [None, None]
+                 for b in range(NB)]
+    pending = [None] * NB
 
     def step(i, ev=None):
         s = i % nset
         if ev is not None:
             ev[0].record()
         if dist is not None:
-            b = i % 2
+            b = i % NB
             if pending[b] is not None:
                 pending[b].wait()          # the gather that last read res2[b] is done
             pb.launch(args2[b][s])
@@ -271,10 +275,10 @@ def time_workload(torch, pb, spec, cfg, P, steps, warmup, dist=None, world=1, us
         if ev is not None:
             ev[1].record()
         if dist is not None:
-            pending[i % 2] = dist.all_gather_into_tensor(gath2[i % 2], res2[i % 2], async_op=True)
+            pending[i % NB] = dist.all_gather_into_tensor(gath2[i % NB], res2[i % NB], async_op=True)
 
     def drain():
-        for b in range(2):
+        for b in range(NB):
             if pending[b] is not None:
                 pending[b].wait()
                 pending[b] = None
@@ -295,8 +299,8 @@ def time_workload(torch, pb, spec, cfg, P, steps, warmup, dist=None, world=1, us
     torch.cuda.synchronize(dev)
     if dist is not None:
         dist.barrier()
-        want = torch.cat([res2[(steps - 1) % 2]] * 1)
-        got = gath2[(steps - 1) % 2]
+        want = res2[(steps - 1) % NB]
+        got = gath2[(steps - 1) % NB]
         r0 = dist.get_rank()
         assert torch.equal(got[r0 * P:(r0 + 1) * P], want), "gathered table does not hold this rank's rows"
     total_ms = e0.elapsed_time(e1)
@@ -437,7 +441,7 @@ def main():
             others[cfg] = {"workload": s2.name, "problems": P2, "evals_per_s": P2 / (r2["ms_per_step"] * 1e-3),
                            "ms_per_step": r2["ms_per_step"], "kernel_ms": r2["kernel_ms"],
                            "algorithmic_gbs": gbs, "roofline_frac": gbs / peak,
-                           "launch": "cuda graph replay" if small else "stream launch",
+                           "launch": "cuda graph replay" if small else "stream launch", "kernel": KERNEL_OF[cfg],
                            "l2": f"ring of {r2['nset']} buffer sets, {r2['footprint_mb']:.0f} MB"}
             pb2.close()
             torch.cuda.empty_cache()
@@ -456,7 +460,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfgd, "clocks": clocks,
             "e2e": e2e, "e2e_resident": e2e_res, "gpu_launches": r["launches"],
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "ntgb::ntg_eval_kernel<kincar>",
+                         "traffic": None, "peak_source": peak_src, "kernel": KERNEL_OF.get(a.workload, "ntgb::ntg_eval_kernel"),
                          "kernel_ms": ms_kernel, "algorithmic_bytes_per_launch": bytes_launch},
             "other_workloads": others,
         }

@@ -530,7 +530,7 @@ int ntgb_create(ntgb_problem **out, const ntgb_setup *s, int device)
             T.one_table = 0;
 
     /* quadrature plan for the cluster kernel (long horizons, one shared table) */
-    T.plan_ptr = nullptr; T.plan = nullptr; T.plan_cl = 0; T.plan_bpc = 0; T.plan_cwin = 0;
+    T.plan_ptr = nullptr; T.plan = nullptr; T.plan_cl = 0; T.plan_bpc = 0; T.plan_cwin = 0; T.plan_n = 0;
     if (T.one_table && nbps > 256 && nbps <= 8 * 224) {
         int CL, bpc;
         ntgb_cluster_geometry(nbps, &CL, &bpc);
@@ -570,6 +570,7 @@ int ntgb_create(ntgb_problem **out, const ntgb_setup *s, int device)
             if (hi >= 0 && hi + T.order[0] - lo > wmax) wmax = hi + T.order[0] - lo;
         }
         T.plan_cwin = wmax * nout;
+        T.plan_n = (int)ent.size();
     }
 
     /* Jacobian row pattern (reference src/colloc.c:243-316) */

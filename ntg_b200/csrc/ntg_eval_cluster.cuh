@@ -34,6 +34,7 @@ namespace cg = cooperative_groups;
 
 struct ClusterSmem {
     int bpc, nbps, S, cwin; /* cwin = doubles of coefficients one CTA stages per problem */
+    int plan_n, plan_cols;  /* quadrature plan kept in shared memory (0 = left in global memory) */
     __host__ __device__ size_t D_off() const { return 0; }                              /* [S][bpc]          */
     __host__ __device__ size_t DI_off() const { return (size_t)S * bpc; }               /* [S]               */
     __host__ __device__ size_t DF_off() const { return DI_off() + S; }                  /* [S]               */
@@ -43,7 +44,8 @@ struct ClusterSmem {
     __host__ __device__ size_t t_off() const { return fall_off() + 2 * (size_t)nbps; }  /* [nbps] (rank 0)   */
     __host__ __device__ size_t dt_off() const { return t_off() + nbps; }                /* [nbps]            */
     __host__ __device__ size_t C_off() const { return dt_off() + nbps; }                /* [2][cwin]         */
-    __host__ __device__ size_t bytes() const { return (C_off() + 2 * (size_t)cwin) * 8 + 16; }
+    __host__ __device__ size_t plan_off() const { return C_off() + 2 * (size_t)cwin; }   /* int2 [plan_n], int [plan_cols+1] */
+    __host__ __device__ size_t bytes() const { return (plan_off() + plan_n) * 8 + (size_t)(plan_cols + 2) * 4 + 16; }
 };
 
 template <class PK>
@@ -56,7 +58,7 @@ __host__ __device__ constexpr bool pk_uniform_outputs()
 
 template <class PK, bool FULL>
 __global__ void __launch_bounds__(256, 1)
-ntg_eval_cluster_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL, int bpc, int cwin)
+ntg_eval_cluster_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL, int bpc, int cwin, int plan_smem)
 {
     constexpr int NOUT = PK::kNout;
     constexpr int NZ = pk_nz<PK>();
@@ -65,7 +67,7 @@ ntg_eval_cluster_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL, int
     extern __shared__ double smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
-    const ClusterSmem L{bpc, T.nbps, T.S, cwin};
+    const ClusterSmem L{bpc, T.nbps, T.S, cwin, plan_smem ? T.plan_n : 0, plan_smem ? T.ncoef[0] : 0};
     const int nbps = T.nbps, nC = T.nC, P = A.P, S = T.S;
     double *D_s = smem + L.D_off();
     double *DI_s = smem + L.DI_off();
@@ -95,6 +97,16 @@ ntg_eval_cluster_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL, int
 
     /* ---- once per CTA ---- */
     for (int i = threadIdx.x; i < nbps - 1; i += blockDim.x) dt_s[i] = __ldg(T.bps + i + 1) - __ldg(T.bps + i);
+    const int2 *plan = T.plan;
+    const int *plan_ptr = T.plan_ptr;
+    if (plan_smem) { /* the plan is re-read for every problem: keep it next to the data it indexes */
+        int2 *pl_s = reinterpret_cast<int2 *>(smem + L.plan_off());
+        int *pp_s = reinterpret_cast<int *>(pl_s + T.plan_n);
+        for (int i = threadIdx.x; i < T.plan_n; i += blockDim.x) pl_s[i] = __ldg(T.plan + i);
+        for (int i = threadIdx.x; i <= T.ncoef[0]; i += blockDim.x) pp_s[i] = __ldg(T.plan_ptr + i);
+        plan = pl_s;
+        plan_ptr = pp_s;
+    }
     if (threadIdx.x == 0) {
         sc_s[0] = sc_s[1] = sc_s[2] = sc_s[3] = 0.0;
         viol_s[0] = 0ull;
@@ -190,9 +202,9 @@ ntg_eval_cluster_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL, int
         pprev = p;
 
         /* ---------------- phase A: this thread's breakpoint ---------------- */
+        double z[NZ]; /* flat outputs of this thread's breakpoint; live across the split barrier */
         if (active) {
             const double *Cp = C_s + (size_t)buf * cwin;
-            double z[NZ];
             double *zp[NOUT];
             /* Zvalue, src/colloc.c:318-326 -- k ascending from 0.0 */
             static_for<0, NOUT>([&](auto jc) {
@@ -221,8 +233,70 @@ ntg_eval_cluster_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL, int
                 }
             });
 
+            int nstate = A.nstate;
+
+            /* unintegrated (trajectory) cost, src/cost.c:99-132 */
+            if constexpr (PK::cb_ucf != nullptr) {
+                if (doU) {
+                    double fv = 0.0;
+                    double df[NZ];
+#pragma unroll
+                    for (int l = 0; l < NZ; l++) df[l] = 0.0;
+                    int mode = mode_obj, i = bp;
+                    PK::cb_ucf(&mode, &nstate, &i, &fv, df, zp);
+                    fall0[buf * nbps + bp] = fv; /* distributed shared memory: rank 0 collects the integrand */
+                    if (obj_d) {
+                        double *Dp = D_s + lbp;
+                        band_from_regs<PK, FULL, true>(T, Bt, df, [&](auto, int, double v) {
+                            *Dp = v;
+                            Dp += bpc;
+                        });
+                    }
+                }
+            }
+            /* initial cost (breakpoint 0: cluster rank 0), src/cost.c:4-36 */
+            if constexpr (PK::cb_icf != nullptr) {
+                if (doI && bp == 0) {
+                    double fv = 0.0;
+                    double df[NZ];
+#pragma unroll
+                    for (int l = 0; l < NZ; l++) df[l] = 0.0;
+                    int mode = mode_obj;
+                    PK::cb_icf(&mode, &nstate, &fv, df, zp);
+                    sc0[buf * 2 + 0] = fv;
+                    if (obj_d) {
+                        double *Dp = DI_s;
+                        band_from_regs<PK, FULL, true>(T, Bt, df, [&](auto, int, double v) { *Dp++ = v; });
+                    }
+                }
+            }
+            /* final cost (last breakpoint: last cluster rank), src/cost.c:141-174 */
+            if constexpr (PK::cb_fcf != nullptr) {
+                if (doF && bp == nbps - 1) {
+                    double fv = 0.0;
+                    double df[NZ];
+#pragma unroll
+                    for (int l = 0; l < NZ; l++) df[l] = 0.0;
+                    int mode = mode_obj;
+                    PK::cb_fcf(&mode, &nstate, &fv, df, zp);
+                    sc0[buf * 2 + 1] = fv;
+                    if (obj_d) {
+                        double *Dp = DF_s;
+                        band_from_regs<PK, FULL, true>(T, Bt, df, [&](auto, int, double v) { *Dp++ = v; });
+                    }
+                }
+            }
+                }
+        /* the quadrature inputs (D, integrand, end-point terms) are written: ARRIVE at the cluster
+         * barrier now and wait only after the Jacobian rows are streamed out, so the release does
+         * not have to drain ~200 outstanding global stores per thread (ncu: 14 % of samples sat in
+         * the fence of a plain cluster.sync() placed after them) */
+        cluster.barrier_arrive();
+        if (active) {
             double viol = 0.0;
             int nstate = A.nstate;
+            double *zp[NOUT];
+            static_for<0, NOUT>([&](auto jc) { zp[decltype(jc)::value] = &z[pk_iz<PK>(decltype(jc)::value)]; });
 
             /* nonlinear trajectory constraints, src/constraints.c:120-162, one ROW per inlined
              * callback: only row m's value and derivatives are consumed in iteration m */
@@ -322,59 +396,8 @@ ntg_eval_cluster_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL, int
             }
             if (viol > 0.0) atomicMax(viol_s + buf, (unsigned long long)__double_as_longlong(viol));
 
-            /* unintegrated (trajectory) cost, src/cost.c:99-132 */
-            if constexpr (PK::cb_ucf != nullptr) {
-                if (doU) {
-                    double fv = 0.0;
-                    double df[NZ];
-#pragma unroll
-                    for (int l = 0; l < NZ; l++) df[l] = 0.0;
-                    int mode = mode_obj, i = bp;
-                    PK::cb_ucf(&mode, &nstate, &i, &fv, df, zp);
-                    fall0[buf * nbps + bp] = fv; /* distributed shared memory: rank 0 collects the integrand */
-                    if (obj_d) {
-                        double *Dp = D_s + lbp;
-                        band_from_regs<PK, FULL, true>(T, Bt, df, [&](auto, int, double v) {
-                            *Dp = v;
-                            Dp += bpc;
-                        });
-                    }
-                }
-            }
-            /* initial cost (breakpoint 0: cluster rank 0), src/cost.c:4-36 */
-            if constexpr (PK::cb_icf != nullptr) {
-                if (doI && bp == 0) {
-                    double fv = 0.0;
-                    double df[NZ];
-#pragma unroll
-                    for (int l = 0; l < NZ; l++) df[l] = 0.0;
-                    int mode = mode_obj;
-                    PK::cb_icf(&mode, &nstate, &fv, df, zp);
-                    sc0[buf * 2 + 0] = fv;
-                    if (obj_d) {
-                        double *Dp = DI_s;
-                        band_from_regs<PK, FULL, true>(T, Bt, df, [&](auto, int, double v) { *Dp++ = v; });
-                    }
-                }
-            }
-            /* final cost (last breakpoint: last cluster rank), src/cost.c:141-174 */
-            if constexpr (PK::cb_fcf != nullptr) {
-                if (doF && bp == nbps - 1) {
-                    double fv = 0.0;
-                    double df[NZ];
-#pragma unroll
-                    for (int l = 0; l < NZ; l++) df[l] = 0.0;
-                    int mode = mode_obj;
-                    PK::cb_fcf(&mode, &nstate, &fv, df, zp);
-                    sc0[buf * 2 + 1] = fv;
-                    if (obj_d) {
-                        double *Dp = DF_s;
-                        band_from_regs<PK, FULL, true>(T, Bt, df, [&](auto, int, double v) { *Dp++ = v; });
-                    }
-                }
-            }
         }
-        cluster.sync(); /* every CTA's D, f and scalars are visible cluster-wide */
+        cluster.barrier_wait(); /* every CTA's D, f and scalars are visible cluster-wide */
 
         /* ------- phase B: one trapezoid chain per gradient column (IntegrateFMatrixCols TRAPEZOID,
          * src/integrator.c:44-48, on the band of src/cost.c:118-132; ascending breakpoint), spread
@@ -393,10 +416,10 @@ ntg_eval_cluster_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL, int
 #pragma unroll
                 for (int j = 0; j < NOUT; j++) { gU[j] = 0.0; dcur[j] = 0.0; }
                 if (doU) {
-                    int e = __ldg(T.plan_ptr + cl);
-                    const int eend = __ldg(T.plan_ptr + cl + 1);
+                    int e = plan_ptr[cl];
+                    const int eend = plan_ptr[cl + 1];
                     if (e < eend) {
-                        int2 en = __ldg(T.plan + e);
+                        int2 en = plan[e];
                         {
                             const int o24 = en.y & 0xffffff, r = en.y >> 24;
                             if (o24 != 0xffffff) {
@@ -406,7 +429,7 @@ ntg_eval_cluster_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL, int
                             }
                         }
                         for (e++; e < eend; e++) {
-                            en = __ldg(T.plan + e);
+                            en = plan[e];
                             const int o24 = en.y & 0xffffff, r = en.y >> 24;
                             const double dt = dt_s[en.x - 1];
                             if (o24 != 0xffffff) {
@@ -469,7 +492,13 @@ int launch_eval_cluster(const ntgb_launch *L)
         if (block > 256) return -1001;
         bool full = true;
         for (int j = 0; j < T.nout; j++) full = full && T.order[j] == PK::kMaxOrd;
-        ClusterSmem lay{bpc, nbps, T.S, L->tab.plan_cwin};
+        ClusterSmem lay{bpc, nbps, T.S, T.plan_cwin, T.plan_n, T.ncoef[0]};
+        int plan_smem = 1;
+        if (lay.bytes() > (size_t)L->max_smem_optin) { /* plan stays in global memory */
+            lay.plan_n = 0;
+            lay.plan_cols = 0;
+            plan_smem = 0;
+        }
         const size_t smem = lay.bytes();
         if (smem > (size_t)L->max_smem_optin) return -1001;
         auto kern = full ? ntg_eval_cluster_kernel<PK, true> : ntg_eval_cluster_kernel<PK, false>;
@@ -490,7 +519,7 @@ int launch_eval_cluster(const ntgb_launch *L)
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, kern, T, L->args, CL, bpc, T.plan_cwin);
+        e = cudaLaunchKernelEx(&cfg, kern, T, L->args, CL, bpc, T.plan_cwin, plan_smem);
         if (e != cudaSuccess) return (int)e;
         return (int)cudaGetLastError();
     }

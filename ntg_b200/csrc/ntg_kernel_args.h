@@ -51,6 +51,7 @@ typedef struct ntgb_devtab {
     const int2 *plan;
     int plan_cl, plan_bpc;          /* cluster geometry the plan was built for               */
     int plan_cwin;                  /* doubles of coefficients the widest CTA stages per problem */
+    int plan_n;                     /* number of plan entries                                */
     double nl_lb_v[NTGB_MAXNLB], nl_ub_v[NTGB_MAXNLB];
 } ntgb_devtab;
 

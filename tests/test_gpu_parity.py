@@ -267,3 +267,60 @@ def test_error_paths_on_gpu(torch_cuda):
     with pytest.raises(NtgError, match="device"):
         Problem(spec, 99)
     pb.close()
+
+
+def _random_spec(rng, family):
+    """Random spline setups around the packs' compile-time shapes: random order / mult /
+    interval count, non-uniform knots, non-uniform breakpoints (first and last on the ends)."""
+    import copy
+    if family == "endpt":
+        base = configs.endpoint()
+        order = [int(rng.integers(3, 7)), int(rng.integers(2, 5))]
+        nbps = int(rng.choice([2, 3, 17, 64, 200, 300]))
+    else:  # kincar: both outputs share one setup (one_table) -> K1s below 257 breakpoints, K1c above
+        base = configs.kincar(20)
+        o = int(rng.integers(3, 6))
+        order = [o, o]
+        nbps = int(rng.choice([40, 257, 300, 449, 700]))
+    spec = copy.deepcopy(base)
+    spec.order = order
+    spec.mult = [int(rng.integers(max(1, md - 1), k)) for k, md in zip(order, spec.maxderiv)]
+    if family == "kincar":
+        spec.mult = [spec.mult[0]] * 2
+        ni = int(rng.integers(1, 40))
+        spec.ninterv = [ni, ni]
+        kn = np.sort(np.concatenate([[0.0, 5.0], rng.uniform(0.0, 5.0, ni - 1)]))
+        spec.knots = [kn, kn.copy()]
+        t1 = 5.0
+    else:
+        spec.ninterv = [int(rng.integers(1, 9)), int(rng.integers(1, 9))]
+        spec.knots = [np.sort(np.concatenate([[0.0, 2.0], rng.uniform(0.0, 2.0, ni - 1)])) for ni in spec.ninterv]
+        t1 = 2.0
+    spec.bps = np.sort(np.concatenate([[0.0, t1], rng.uniform(0.0, t1, nbps - 2)])) if nbps > 2 else np.array([0.0, t1])
+    spec.nbps = nbps
+    spec.name = f"random_{family}"
+    return spec
+
+
+@pytest.mark.parametrize("seed", list(range(14)))
+def test_random_shapes(torch_cuda, port, seed, monkeypatch):
+    rng = np.random.default_rng(1000 + seed)
+    family = "endpt" if seed % 2 == 0 else "kincar"
+    spec = _random_spec(rng, family)
+    if seed % 4 == 2:
+        monkeypatch.setenv("NTG_B200_KERNEL", "general")
+    P = int(rng.choice([1, 5, 37]))
+    X = rng.uniform(-2.0, 2.0, (P, spec.nC))
+    o = port.eval(spec, X, dense=False, band=True)
+    pb, r = gpu_eval(torch_cuda, spec, X, False, want_Z=False)
+    B, off, _ = pb.tables()
+    Bo, offo, col0o = port.tables(spec)
+    for a, b in zip(B, Bo):
+        assert_bitexact(a, b, "K0 table")
+    assert_bitexact(off, offo, "offsets")
+    assert_bitexact(pb.pattern()[0], col0o, "pattern")
+    cmp = assert_close if family == "endpt" else assert_bitexact   # endpt calls libm
+    for k in ("f", "g", "c", "Jband"):
+        cmp(r[k], o[k], f"seed {seed} ({family}, order {spec.order}, mult {spec.mult}, "
+                        f"ninterv {spec.ninterv}, nbps {spec.nbps}, P {P}): {k}")
+    pb.close()

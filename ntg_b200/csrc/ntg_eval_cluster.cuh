@@ -409,12 +409,19 @@ ntg_eval_cluster_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL, int
             const int last_rank = (nbps - 1) / bpc;
             const int off_last = __ldg(T.off[0] + nbps - 1);
             const int jpitch = order0 * bpc; /* one output's block of D */
-            /* one item = local column cl of ALL outputs: the plan (which breakpoints, which band
-             * position) is shared, so it is decoded once and drives NOUT independent chains */
-            for (int cl = rank * (int)blockDim.x + (int)threadIdx.x; cl < ncoef0; cl += CL * (int)blockDim.x) {
-                double gU[NOUT], dcur[NOUT];
+            /* one item = local column cl of a GROUP of outputs: the plan (which breakpoints, which
+             * band position) is shared by all outputs, so it is decoded once and drives JG independent
+             * chains (measured: groups of 2 outputs balance the threads better but lose more to the extra decodes) */
+            constexpr int JG = NOUT;
+            constexpr int NG = NOUT / JG;
+            const int nitems = ncoef0 * NG;
+            for (int it = rank * (int)blockDim.x + (int)threadIdx.x; it < nitems; it += CL * (int)blockDim.x) {
+                const int jg = it / ncoef0;
+                const int cl = it - jg * ncoef0;
+                const int jbase = jg * JG * jpitch; /* first output of the group inside D */
+                double gU[JG], dcur[JG];
 #pragma unroll
-                for (int j = 0; j < NOUT; j++) { gU[j] = 0.0; dcur[j] = 0.0; }
+                for (int j = 0; j < JG; j++) { gU[j] = 0.0; dcur[j] = 0.0; }
                 if (doU) {
                     int e = plan_ptr[cl];
                     const int eend = plan_ptr[cl + 1];
@@ -423,41 +430,49 @@ ntg_eval_cluster_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL, int
                         {
                             const int o24 = en.y & 0xffffff, r = en.y >> 24;
                             if (o24 != 0xffffff) {
-                                const double *base = ((r == rank) ? D_s : cluster.map_shared_rank(D_s, r)) + o24;
+                                if (r == rank) { /* own shared memory: plain LDS */
 #pragma unroll
-                                for (int j = 0; j < NOUT; j++) dcur[j] = base[j * jpitch];
+                                    for (int j = 0; j < JG; j++) dcur[j] = D_s[jbase + j * jpitch + o24];
+                                } else {         /* neighbour CTA: distributed shared memory */
+                                    const double *base = cluster.map_shared_rank(D_s, r) + jbase + o24;
+#pragma unroll
+                                    for (int j = 0; j < JG; j++) dcur[j] = base[j * jpitch];
+                                }
                             }
                         }
                         for (e++; e < eend; e++) {
                             en = plan[e];
                             const int o24 = en.y & 0xffffff, r = en.y >> 24;
                             const double dt = dt_s[en.x - 1];
-                            if (o24 != 0xffffff) {
-                                const double *base = ((r == rank) ? D_s : cluster.map_shared_rank(D_s, r)) + o24;
+                            double dn[JG];
+                            if (o24 == 0xffffff) {
 #pragma unroll
-                                for (int j = 0; j < NOUT; j++) {
-                                    const double dn = base[j * jpitch];
-                                    gU[j] = gU[j] + (dt * (dn + dcur[j])) / 2;
-                                    dcur[j] = dn;
-                                }
+                                for (int j = 0; j < JG; j++) dn[j] = 0.0;
+                            } else if (r == rank) {
+#pragma unroll
+                                for (int j = 0; j < JG; j++) dn[j] = D_s[jbase + j * jpitch + o24];
                             } else {
+                                const double *base = cluster.map_shared_rank(D_s, r) + jbase + o24;
 #pragma unroll
-                                for (int j = 0; j < NOUT; j++) {
-                                    gU[j] = gU[j] + (dt * (0.0 + dcur[j])) / 2;
-                                    dcur[j] = 0.0;
-                                }
+                                for (int j = 0; j < JG; j++) dn[j] = base[j * jpitch];
+                            }
+#pragma unroll
+                            for (int j = 0; j < JG; j++) {
+                                gU[j] = gU[j] + (dt * (dn[j] + dcur[j])) / 2;
+                                dcur[j] = dn[j];
                             }
                         }
                     }
                 }
                 const int kF = cl - off_last;
 #pragma unroll
-                for (int j = 0; j < NOUT; j++) {
-                    const int s0 = j * order0; /* jk0_j: every output has the same order */
+                for (int j = 0; j < JG; j++) {
+                    const int jo = jg * JG + j;
+                    const int s0 = jo * order0; /* jk0_j: every output has the same order */
                     double gI = 0.0, gF = 0.0;
                     if (doI && cl < order0) gI = cluster.map_shared_rank(DI_s, 0)[s0 + cl]; /* offset 0, src/colloc.c:254 */
                     if (doF && kF >= 0 && kF < order0) gF = cluster.map_shared_rank(DF_s, last_rank)[s0 + kF];
-                    st_stream(A.g + (size_t)p * nC + (size_t)j * ncoef0 + cl, (gI + gU[j]) + gF);
+                    st_stream(A.g + (size_t)p * nC + (size_t)jo * ncoef0 + cl, (gI + gU[j]) + gF);
                 }
             }
         }

@@ -102,14 +102,16 @@ struct ntgb_problem {
     double *daug[NTGB_MAXOUT] = {nullptr};
     double *dknots[NTGB_MAXOUT] = {nullptr};
     std::vector<void *> allocs;
-    /* scratch for ntgb_eval_host */
-    struct {
-        int P = 0, jac_layout = -1;
+    /* scratch for ntgb_eval_host: two device buffer sets of `cap` problems each, one stream each,
+     * so chunk k+1's H2D/compute overlaps chunk k's D2H */
+    struct HostScratch {
+        int cap = 0, jac_layout = -1;
+        bool hasZ = false;
         double *C = nullptr, *f = nullptr, *g = nullptr, *c = nullptr, *J = nullptr, *Z = nullptr,
                *result = nullptr;
         size_t Jbytes = 0;
-    } hs;
-    cudaStream_t hstream = nullptr;
+        cudaStream_t stream = nullptr;
+    } hs[2];
 };
 
 namespace {
@@ -326,10 +328,12 @@ void ntgb_destroy(ntgb_problem *pb)
     if (!pb) return;
     DeviceGuard dg(pb->device);
     for (void *p : pb->allocs) cudaFree(p);
-    double *hsp[] = {pb->hs.C, pb->hs.f, pb->hs.g, pb->hs.c, pb->hs.J, pb->hs.Z, pb->hs.result};
-    for (double *p : hsp)
-        if (p) cudaFree(p);
-    if (pb->hstream) cudaStreamDestroy(pb->hstream);
+    for (auto &h : pb->hs) {
+        double *hsp[] = {h.C, h.f, h.g, h.c, h.J, h.Z, h.result};
+        for (double *p : hsp)
+            if (p) cudaFree(p);
+        if (h.stream) cudaStreamDestroy(h.stream);
+    }
     delete pb;
 }
 
@@ -739,53 +743,73 @@ int ntgb_eval_host(ntgb_problem *pb, const ntgb_eval_args *h)
     DeviceGuard dg(pb->device);
     if (!dg.ok) return fail(NTGB_ECUDA, "cannot select device %d", pb->device);
     const ntgb_dims &d = pb->dims;
-    const size_t P = (size_t)h->P;
-    auto &s = pb->hs;
-    if (!pb->hstream) CUDA_TRY(cudaStreamCreateWithFlags(&pb->hstream, cudaStreamNonBlocking));
     const size_t jper = h->jac_layout == NTGB_JAC_DENSE ? (size_t)d.ncnln * d.nC
                       : h->jac_layout == NTGB_JAC_BAND  ? (size_t)d.ncnln * d.sorder : 0;
-    if (h->P > s.P || (h->J && (s.jac_layout != h->jac_layout || s.Jbytes < P * jper * sizeof(double))) ||
-        (h->Z && !s.Z)) {
+    /* chunking: one chunk for small batches (an NPSOL callback is P = 1); otherwise chunks of
+     * >= 1024 problems and ~64 MB of results, alternating between the two buffer sets so copies
+     * overlap compute.  Host buffers should be page-locked (cudaHostRegister / cudaMallocHost)
+     * for the copies to be asynchronous; pageable memory works, without the overlap. */
+    const size_t per = sizeof(double) * ((size_t)2 * d.nC + 3 + (size_t)(d.ncnln > 0 ? d.ncnln : 1) +
+                                         (h->J ? jper : 0) + (h->Z ? (size_t)d.nZ : 0));
+    long long chunk = (long long)((64ull << 20) / (per ? per : 1));
+    if (chunk < 1024) chunk = 1024;
+    if (chunk > h->P) chunk = h->P;
+    const int nbuf = chunk < h->P ? 2 : 1;
+    for (int b = 0; b < nbuf; b++) {
+        auto &s = pb->hs[b];
+        if (!s.stream) CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        const bool grow = chunk > s.cap || (h->J && (s.jac_layout != h->jac_layout || s.Jbytes < (size_t)chunk * jper * sizeof(double))) ||
+                          (h->Z && !s.hasZ);
+        if (!grow) continue;
         double **ptrs[] = {&s.C, &s.f, &s.g, &s.c, &s.J, &s.Z, &s.result};
         for (double **pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
-        const size_t cap = P;
+        const size_t cap = (size_t)chunk;
         CUDA_TRY(cudaMalloc((void **)&s.C, cap * d.nC * sizeof(double)));
         CUDA_TRY(cudaMalloc((void **)&s.f, cap * sizeof(double)));
         CUDA_TRY(cudaMalloc((void **)&s.g, cap * d.nC * sizeof(double)));
         CUDA_TRY(cudaMalloc((void **)&s.c, cap * (size_t)(d.ncnln > 0 ? d.ncnln : 1) * sizeof(double)));
         CUDA_TRY(cudaMalloc((void **)&s.result, cap * 2 * sizeof(double)));
-        if (h->Z) CUDA_TRY(cudaMalloc((void **)&s.Z, cap * d.nZ * sizeof(double)));
+        s.hasZ = false;
+        if (h->Z) { CUDA_TRY(cudaMalloc((void **)&s.Z, cap * d.nZ * sizeof(double))); s.hasZ = true; }
         s.Jbytes = 0;
         if (h->J && jper) {
             s.Jbytes = cap * jper * sizeof(double);
             CUDA_TRY(cudaMalloc((void **)&s.J, s.Jbytes));
-            /* out-of-band entries are zeroed once, as the reference's calloc does (src/ntg.c:218) */
-            CUDA_TRY(cudaMemsetAsync(s.J, 0, s.Jbytes, pb->hstream));
+            /* out-of-band entries are zeroed once, as the reference's calloc does (src/ntg.c:218);
+             * the band positions are the same for every problem, so reuse across chunks is safe */
+            CUDA_TRY(cudaMemsetAsync(s.J, 0, s.Jbytes, s.stream));
         }
-        s.P = (int)cap;
+        s.cap = (int)cap;
         s.jac_layout = h->jac_layout;
     }
-    CUDA_TRY(cudaMemcpyAsync(s.C, h->C, P * d.nC * sizeof(double), cudaMemcpyHostToDevice, pb->hstream));
-    ntgb_eval_args a = *h;
-    a.C = s.C;
-    a.f = h->f ? s.f : nullptr;
-    a.g = h->g ? s.g : nullptr;
-    a.c = h->c ? s.c : nullptr;
-    a.J = h->J ? s.J : nullptr;
-    a.Z = h->Z ? s.Z : nullptr;
-    a.result = h->result ? s.result : nullptr;
-    a.stream = pb->hstream;
-    const int rc = ntgb_eval(pb, &a);
-    if (rc) return rc;
     const bool ov = h->mode_obj == 0 || h->mode_obj == 2, od = h->mode_obj == 1 || h->mode_obj == 2;
     const bool cv = h->mode_con == 0 || h->mode_con == 2, cd = h->mode_con == 1 || h->mode_con == 2;
-    if (h->f && ov) CUDA_TRY(cudaMemcpyAsync(h->f, s.f, P * sizeof(double), cudaMemcpyDeviceToHost, pb->hstream));
-    if (h->g && od) CUDA_TRY(cudaMemcpyAsync(h->g, s.g, P * d.nC * sizeof(double), cudaMemcpyDeviceToHost, pb->hstream));
-    if (h->c && cv && d.ncnln) CUDA_TRY(cudaMemcpyAsync(h->c, s.c, P * d.ncnln * sizeof(double), cudaMemcpyDeviceToHost, pb->hstream));
-    if (h->J && cd && jper) CUDA_TRY(cudaMemcpyAsync(h->J, s.J, P * jper * sizeof(double), cudaMemcpyDeviceToHost, pb->hstream));
-    if (h->Z) CUDA_TRY(cudaMemcpyAsync(h->Z, s.Z, P * d.nZ * sizeof(double), cudaMemcpyDeviceToHost, pb->hstream));
-    if (h->result) CUDA_TRY(cudaMemcpyAsync(h->result, s.result, P * 2 * sizeof(double), cudaMemcpyDeviceToHost, pb->hstream));
-    CUDA_TRY(cudaStreamSynchronize(pb->hstream));
+    int k = 0;
+    for (long long lo = 0; lo < h->P; lo += chunk, k++) {
+        auto &s = pb->hs[k % nbuf];
+        const size_t n = (size_t)((h->P - lo) < chunk ? (h->P - lo) : chunk);
+        cudaStream_t st = s.stream;
+        CUDA_TRY(cudaMemcpyAsync(s.C, h->C + (size_t)lo * d.nC, n * d.nC * sizeof(double), cudaMemcpyHostToDevice, st));
+        ntgb_eval_args a = *h;
+        a.P = (int)n;
+        a.C = s.C;
+        a.f = h->f ? s.f : nullptr;
+        a.g = h->g ? s.g : nullptr;
+        a.c = h->c ? s.c : nullptr;
+        a.J = h->J ? s.J : nullptr;
+        a.Z = h->Z ? s.Z : nullptr;
+        a.result = h->result ? s.result : nullptr;
+        a.stream = st;
+        const int rc = ntgb_eval(pb, &a);
+        if (rc) return rc;
+        if (h->f && ov) CUDA_TRY(cudaMemcpyAsync(h->f + lo, s.f, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (h->g && od) CUDA_TRY(cudaMemcpyAsync(h->g + (size_t)lo * d.nC, s.g, n * d.nC * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (h->c && cv && d.ncnln) CUDA_TRY(cudaMemcpyAsync(h->c + (size_t)lo * d.ncnln, s.c, n * d.ncnln * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (h->J && cd && jper) CUDA_TRY(cudaMemcpyAsync(h->J + (size_t)lo * jper, s.J, n * jper * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (h->Z) CUDA_TRY(cudaMemcpyAsync(h->Z + (size_t)lo * d.nZ, s.Z, n * d.nZ * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (h->result) CUDA_TRY(cudaMemcpyAsync(h->result + (size_t)lo * 2, s.result, n * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    for (int b = 0; b < nbuf; b++) CUDA_TRY(cudaStreamSynchronize(pb->hs[b].stream));
     return 0;
 }
 

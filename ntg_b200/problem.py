@@ -215,6 +215,20 @@ class Problem:
         out["c"] = out["c"][:, :d.ncnln]
         return out
 
+    def eval_host_tensors(self, Xh, out, mode_obj=2, mode_con=2, jac=JAC_BAND, nstate=0):
+        """ntgb_eval_host on (ideally pinned) host torch tensors: Xh [P][nC]; out: dict with any of
+        f [P], g [P][nC], c [P][ncnln], J [P][ncnln*S or nC*ncnln], result [P][2]."""
+        a = NtgbEvalArgs()
+        a.P = int(Xh.shape[0])
+        a.C = Xh.data_ptr()
+        a.mode_obj, a.mode_con, a.nstate = mode_obj, mode_con, nstate
+        a.f, a.g, a.c = _ptr(out.get("f")), _ptr(out.get("g")), _ptr(out.get("c"))
+        a.J = _ptr(out.get("J"))
+        a.jac_layout = jac if out.get("J") is not None else JAC_NONE
+        a.Z = _ptr(out.get("Z"))
+        a.result = _ptr(out.get("result"))
+        _check(core().ntgb_eval_host(self._h, C.byref(a)))
+
     # ---- band <-> (row, col, value) ----
     def band_to_rows(self, Jband: np.ndarray) -> np.ndarray:
         """device band layout [P][ncnln*S] (trajectory rows breakpoint-fastest) ->

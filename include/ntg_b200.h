@@ -128,6 +128,10 @@ typedef struct ntgb_eval_args {
     double *Z;           /* [P][nZ] flat outputs and derivatives, or NULL      */
     double *result;      /* [P][2] = (objective, max nonlinear violation), or NULL */
     void *stream;        /* cudaStream_t                                       */
+    int *abort_flag;     /* optional device int: set to 1 when any callback asks to stop by
+                          * writing *mode = -1 (reference src/ntg.c:369: NPSOL then terminates);
+                          * the caller zeroes it.  ntgb_eval_host manages its own and returns
+                          * NTGB_EABORT.                                        */
 } ntgb_eval_args;
 
 /* error codes */
@@ -137,6 +141,7 @@ typedef struct ntgb_eval_args {
 #define NTGB_ECUDA    -3  /* CUDA runtime failure (includes: no device)        */
 #define NTGB_ELIMIT   -4  /* problem exceeds the pack's compile-time bounds    */
 #define NTGB_ENOMEM   -5
+#define NTGB_EABORT   -6  /* a callback set *mode = -1 (only from ntgb_eval_host)  */
 
 const char *ntgb_last_error(void);
 const char *ntgb_version(void);

@@ -73,6 +73,7 @@ class NtgbEvalArgs(C.Structure):
         ("Z", C.c_void_p),
         ("result", C.c_void_p),
         ("stream", C.c_void_p),
+        ("abort_flag", C.c_void_p),
     ]
 
 

@@ -112,6 +112,7 @@ struct ntgb_problem {
         size_t Jbytes = 0;
         cudaStream_t stream = nullptr;
     } hs[2];
+    int *d_abort = nullptr; /* device flag: a callback wrote *mode = -1 */
 };
 
 namespace {
@@ -784,6 +785,9 @@ int ntgb_eval_host(ntgb_problem *pb, const ntgb_eval_args *h)
     }
     const bool ov = h->mode_obj == 0 || h->mode_obj == 2, od = h->mode_obj == 1 || h->mode_obj == 2;
     const bool cv = h->mode_con == 0 || h->mode_con == 2, cd = h->mode_con == 1 || h->mode_con == 2;
+    if (!pb->d_abort) { if (int rc0 = dev_alloc(pb, &pb->d_abort, 1)) return rc0; }
+    CUDA_TRY(cudaMemsetAsync(pb->d_abort, 0, sizeof(int), pb->hs[0].stream));
+    if (nbuf > 1) CUDA_TRY(cudaStreamSynchronize(pb->hs[0].stream)); /* the other stream must see the zero */
     int k = 0;
     for (long long lo = 0; lo < h->P; lo += chunk, k++) {
         auto &s = pb->hs[k % nbuf];
@@ -800,6 +804,7 @@ int ntgb_eval_host(ntgb_problem *pb, const ntgb_eval_args *h)
         a.Z = h->Z ? s.Z : nullptr;
         a.result = h->result ? s.result : nullptr;
         a.stream = st;
+        a.abort_flag = pb->d_abort;
         const int rc = ntgb_eval(pb, &a);
         if (rc) return rc;
         if (h->f && ov) CUDA_TRY(cudaMemcpyAsync(h->f + lo, s.f, n * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -809,7 +814,13 @@ int ntgb_eval_host(ntgb_problem *pb, const ntgb_eval_args *h)
         if (h->Z) CUDA_TRY(cudaMemcpyAsync(h->Z + (size_t)lo * d.nZ, s.Z, n * d.nZ * sizeof(double), cudaMemcpyDeviceToHost, st));
         if (h->result) CUDA_TRY(cudaMemcpyAsync(h->result + (size_t)lo * 2, s.result, n * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
+    int aborted = 0;
+    CUDA_TRY(cudaMemcpyAsync(&aborted, pb->d_abort, sizeof(int), cudaMemcpyDeviceToHost, pb->hs[(k - 1) % nbuf].stream));
     for (int b = 0; b < nbuf; b++) CUDA_TRY(cudaStreamSynchronize(pb->hs[b].stream));
+    if (nbuf > 1 && !aborted) { /* the flag copy ran on one stream; re-read after both finished */
+        CUDA_TRY(cudaMemcpy(&aborted, pb->d_abort, sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    if (aborted) return fail(NTGB_EABORT, "a callback set *mode = -1");
     return 0;
 }
 

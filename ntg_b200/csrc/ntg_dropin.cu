@@ -51,7 +51,10 @@ void np_funobj(int *mode, int *n, double *x, double *y, double *yprime, int *nst
     memset(&a, 0, sizeof a);
     a.P = 1; a.C = x; a.mode_obj = *mode; a.mode_con = -1; a.nstate = *nstate;
     a.f = y; a.g = yprime; a.jac_layout = NTGB_JAC_NONE;
-    if (ntgb_eval_host(g_pb, &a) != 0) {
+    const int rc = ntgb_eval_host(g_pb, &a);
+    if (rc == NTGB_EABORT) {
+        *mode = -1; /* the user's callback asked NPSOL to stop, as in the reference */
+    } else if (rc != 0) {
         fprintf(stderr, "ntg: objective evaluation failed: %s\n", ntgb_last_error());
         g_eval_error = 1;
         *mode = -1;
@@ -67,7 +70,10 @@ void np_funcon(int *mode, int *ncnln, int *n, int *nrowj, int *needc, double *x,
     memset(&a, 0, sizeof a);
     a.P = 1; a.C = x; a.mode_obj = -1; a.mode_con = *mode; a.nstate = *nstate;
     a.c = c; a.J = cjac; a.jac_layout = NTGB_JAC_DENSE;
-    if (ntgb_eval_host(g_pb, &a) != 0) {
+    const int rc = ntgb_eval_host(g_pb, &a);
+    if (rc == NTGB_EABORT) {
+        *mode = -1;
+    } else if (rc != 0) {
         fprintf(stderr, "ntg: constraint evaluation failed: %s\n", ntgb_last_error());
         g_eval_error = 1;
         *mode = -1;

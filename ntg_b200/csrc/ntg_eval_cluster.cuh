@@ -244,6 +244,7 @@ ntg_eval_cluster_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL, int
                     for (int l = 0; l < NZ; l++) df[l] = 0.0;
                     int mode = mode_obj, i = bp;
                     PK::cb_ucf(&mode, &nstate, &i, &fv, df, zp);
+                    note_abort(A, mode);
                     fall0[buf * nbps + bp] = fv; /* distributed shared memory: rank 0 collects the integrand */
                     if (obj_d) {
                         double *Dp = D_s + lbp;
@@ -263,6 +264,7 @@ ntg_eval_cluster_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL, int
                     for (int l = 0; l < NZ; l++) df[l] = 0.0;
                     int mode = mode_obj;
                     PK::cb_icf(&mode, &nstate, &fv, df, zp);
+                    note_abort(A, mode);
                     sc0[buf * 2 + 0] = fv;
                     if (obj_d) {
                         double *Dp = DI_s;
@@ -279,6 +281,7 @@ ntg_eval_cluster_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL, int
                     for (int l = 0; l < NZ; l++) df[l] = 0.0;
                     int mode = mode_obj;
                     PK::cb_fcf(&mode, &nstate, &fv, df, zp);
+                    note_abort(A, mode);
                     sc0[buf * 2 + 1] = fv;
                     if (obj_d) {
                         double *Dp = DF_s;
@@ -316,6 +319,7 @@ ntg_eval_cluster_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL, int
                         }
                         int mode = mode_con, i = bp;
                         PK::cb_nltcf(&mode, &nstate, &i, cv, dfp, zp);
+                        note_abort(A, mode);
                         if (con_v) {
                             if (A.c != nullptr)
                                 st_stream(A.c + (size_t)p * T.ncnln + T.nnlic + (size_t)m * nbps + bp, cv[m]);
@@ -357,6 +361,7 @@ ntg_eval_cluster_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL, int
                     }
                     int mode = mode_con;
                     PK::cb_nlicf(&mode, &nstate, cv, dfp, zp);
+                    note_abort(A, mode);
                     if (con_v) {
 #pragma unroll
                         for (int m = 0; m < PK::kNnlic; m++) {
@@ -383,6 +388,7 @@ ntg_eval_cluster_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL, int
                     int mode = mode_con;
                     const int rb = T.nnlic + T.nnltc * nbps;
                     PK::cb_nlfcf(&mode, &nstate, cv, dfp, zp);
+                    note_abort(A, mode);
                     if (con_v) {
 #pragma unroll
                         for (int m = 0; m < PK::kNnlfc; m++) {

@@ -62,6 +62,12 @@ __host__ __device__ constexpr int pk_nz() { return pk_iz<PK>(PK::kNout); }
 
 __device__ __forceinline__ void st_stream(double *p, double v) { __stcs(p, v); }
 
+/* a callback that writes *mode = -1 asks the solver to stop (reference src/ntg.c:369) */
+__device__ __forceinline__ void note_abort(const ntgb_eval_args &A, int mode)
+{
+    if (mode < 0 && A.abort_flag != nullptr) *A.abort_flag = 1;
+}
+
 /* shared-memory carve-up for one tile of G problems */
 struct SmemLayout {
     int G, nbps, nz;
@@ -238,6 +244,7 @@ __global__ void __launch_bounds__(256) ntg_eval_kernel(const ntgb_devtab T, cons
                     }
                     int mode = mode_con, i = bp;
                     PK::cb_nltcf(&mode, &nstate, &i, cv, dfp, zp);
+                    note_abort(A, mode);
                     if (con_v) {
 #pragma unroll
                         for (int m = 0; m < PK::kNnltc; m++) {
@@ -265,6 +272,7 @@ __global__ void __launch_bounds__(256) ntg_eval_kernel(const ntgb_devtab T, cons
                     }
                     int mode = mode_con;
                     PK::cb_nlicf(&mode, &nstate, cv, dfp, zp);
+                    note_abort(A, mode);
                     if (con_v) {
 #pragma unroll
                         for (int m = 0; m < PK::kNnlic; m++) {
@@ -291,6 +299,7 @@ __global__ void __launch_bounds__(256) ntg_eval_kernel(const ntgb_devtab T, cons
                     int mode = mode_con;
                     const int rb = T.nnlic + T.nnltc * nbps;
                     PK::cb_nlfcf(&mode, &nstate, cv, dfp, zp);
+                    note_abort(A, mode);
                     if (con_v) {
 #pragma unroll
                         for (int m = 0; m < PK::kNnlfc; m++) {
@@ -313,6 +322,7 @@ __global__ void __launch_bounds__(256) ntg_eval_kernel(const ntgb_devtab T, cons
                     for (int l = 0; l < NZ; l++) df[l] = 0.0;
                     int mode = mode_obj, i = bp;
                     PK::cb_ucf(&mode, &nstate, &i, &fv, df, zp);
+                    note_abort(A, mode);
                     f_s[q] = fv;
                     if (obj_d) {
 #pragma unroll
@@ -329,6 +339,7 @@ __global__ void __launch_bounds__(256) ntg_eval_kernel(const ntgb_devtab T, cons
                     for (int l = 0; l < NZ; l++) df[l] = 0.0;
                     int mode = mode_obj;
                     PK::cb_icf(&mode, &nstate, &fv, df, zp);
+                    note_abort(A, mode);
                     cI_s[pl] = fv;
 #pragma unroll
                     for (int l = 0; l < NZ; l++) dfI_s[pl * NZ + l] = df[l];
@@ -343,6 +354,7 @@ __global__ void __launch_bounds__(256) ntg_eval_kernel(const ntgb_devtab T, cons
                     for (int l = 0; l < NZ; l++) df[l] = 0.0;
                     int mode = mode_obj;
                     PK::cb_fcf(&mode, &nstate, &fv, df, zp);
+                    note_abort(A, mode);
                     cF_s[pl] = fv;
 #pragma unroll
                     for (int l = 0; l < NZ; l++) dfF_s[pl * NZ + l] = df[l];

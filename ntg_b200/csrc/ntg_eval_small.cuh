@@ -291,6 +291,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                         }
                         int mode = mode_con, i = bp;
                         PK::cb_nltcf(&mode, &nstate, &i, cv, dfp, zp);
+                        note_abort(A, mode);
                         if (con_v) {
                             double *cp = A.c + (size_t)p * T.ncnln + T.nnlic + bp;
 #pragma unroll
@@ -318,6 +319,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                         }
                         int mode = mode_con;
                         PK::cb_nlicf(&mode, &nstate, cv, dfp, zp);
+                        note_abort(A, mode);
                         if (con_v) {
 #pragma unroll
                             for (int m = 0; m < PK::kNnlic; m++) {
@@ -344,6 +346,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                         int mode = mode_con;
                         const int rb = T.nnlic + T.nnltc * nbps;
                         PK::cb_nlfcf(&mode, &nstate, cv, dfp, zp);
+                        note_abort(A, mode);
                         if (con_v) {
 #pragma unroll
                             for (int m = 0; m < PK::kNnlfc; m++) {
@@ -367,6 +370,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                         for (int l = 0; l < NZ; l++) df[l] = 0.0;
                         int mode = mode_obj, i = bp;
                         PK::cb_ucf(&mode, &nstate, &i, &fv, df, zp);
+                        note_abort(A, mode);
                         f_s[bp * GRP + plr] = fv;
                         if (obj_d) {
                             double *Dp = D_s + (size_t)bp * GRP + plr;
@@ -387,6 +391,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                         for (int l = 0; l < NZ; l++) df[l] = 0.0;
                         int mode = mode_obj;
                         PK::cb_icf(&mode, &nstate, &fv, df, zp);
+                        note_abort(A, mode);
                         cI_s[plr] = fv;
                         if (obj_d) {
                             double *Dp = DI_s + plr * S;
@@ -403,6 +408,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                         for (int l = 0; l < NZ; l++) df[l] = 0.0;
                         int mode = mode_obj;
                         PK::cb_fcf(&mode, &nstate, &fv, df, zp);
+                        note_abort(A, mode);
                         cF_s[plr] = fv;
                         if (obj_d) {
                             double *Dp = DF_s + plr * S;

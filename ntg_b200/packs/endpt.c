@@ -45,6 +45,9 @@ void ep_ucf(int *mode, int *nstate, int *i, double *f, double *df, double **zp)
         df[3] = s;
         df[4] = 2.0 * w * Q1;
     }
+    /* a callback may ask the solver to stop by setting *mode = -1 (reference src/ntg.c:369) */
+    if (P0 > 1.0e6)
+        *mode = -1;
 }
 
 void ep_fcf(int *mode, int *nstate, double *f, double *df, double **zp)

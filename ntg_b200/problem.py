@@ -165,7 +165,8 @@ class Problem:
             out["Z"] = mk((P, d.nZ), dtype=torch.float64, device=dev)
         return out
 
-    def eval_args(self, Cdev, out, mode_obj=2, mode_con=2, jac=JAC_BAND, nstate=0, stream=None) -> NtgbEvalArgs:
+    def eval_args(self, Cdev, out, mode_obj=2, mode_con=2, jac=JAC_BAND, nstate=0, stream=None,
+                  abort_flag=None) -> NtgbEvalArgs:
         a = NtgbEvalArgs()
         a.P = int(Cdev.shape[0])
         a.C = Cdev.data_ptr()
@@ -176,6 +177,7 @@ class Problem:
         a.Z = _ptr(out.get("Z"))
         a.result = _ptr(out.get("result"))
         a.stream = stream
+        a.abort_flag = _ptr(abort_flag)
         return a
 
     def launch(self, args: NtgbEvalArgs):

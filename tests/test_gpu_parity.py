@@ -324,3 +324,29 @@ def test_random_shapes(torch_cuda, port, seed, monkeypatch):
         cmp(r[k], o[k], f"seed {seed} ({family}, order {spec.order}, mult {spec.mult}, "
                         f"ninterv {spec.ninterv}, nbps {spec.nbps}, P {P}): {k}")
     pb.close()
+
+
+def test_callback_abort_request(torch_cuda):
+    """A callback that writes *mode = -1 asks the solver to stop (reference src/ntg.c:369): the
+    device path raises the abort flag, ntgb_eval_host returns NTGB_EABORT."""
+    import torch
+    from ntg_b200 import Problem
+    from ntg_b200.problem import NtgError
+    spec, X = golden_spec("endpoint")
+    pb = Problem(spec, 0)
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    Xd = torch.from_numpy(X).cuda()
+    out = pb.alloc_outputs(X.shape[0])
+    st = torch.cuda.current_stream().cuda_stream
+    pb.launch(pb.eval_args(Xd, out, stream=st, abort_flag=flag))
+    torch.cuda.synchronize()
+    assert int(flag.item()) == 0
+    Xbad = X.copy()
+    Xbad[3, :] = 1.0e7          # ep_ucf sets *mode = -1 when zp[0][0] > 1e6
+    pb.launch(pb.eval_args(torch.from_numpy(Xbad).cuda(), out, stream=st, abort_flag=flag))
+    torch.cuda.synchronize()
+    assert int(flag.item()) == 1
+    with pytest.raises(NtgError, match="-6"):
+        pb.eval_host(Xbad)
+    pb.eval_host(X)              # and the next clean call succeeds again
+    pb.close()

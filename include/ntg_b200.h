@@ -187,6 +187,22 @@ int  ntgb_eval_linear(ntgb_problem *pb, int P, const double *C, double *lin,
 int  ntgb_spline_interp(ntgb_problem *pb, int P, const double *C, int nt,
                         const double *t, double *out, void *stream);
 
+/*
+ * Batched merit line search -- first step towards a batched SQP consumer
+ * (NPSOL's line search is serial and proprietary).
+ * For every problem p and every trial step alpha[a] (device array, tried in the
+ * given order) evaluates x = C[p] + alpha[a]*dC[p] in values-only mode, P*nalpha
+ * evaluations in ONE launch of the evaluator, and the L-infinity merit
+ *     phi = f + mu * max(max nonlinear violation, max linear violation).
+ * Per problem it selects the first alpha with phi <= phi0[p] + c1*alpha*dphi0[p]
+ * (Armijo; phi0/dphi0 device arrays, dphi0 may be NULL = plain decrease), else
+ * the alpha of smallest phi.  Outputs (device, any may be NULL): alpha_best[P],
+ * phi_best[P], C_new[P][nC] = C + alpha_best*dC.  Asynchronous on `stream`.
+ */
+int  ntgb_linesearch(ntgb_problem *pb, int P, const double *C, const double *dC, int nalpha,
+                     const double *alpha, double mu, double c1, const double *phi0, const double *dphi0,
+                     double *alpha_best, double *phi_best, double *C_new, void *stream);
+
 /* ---- callback packs ------------------------------------------------------ */
 /*
  * A pack is a shared object produced by tools/ntg_pack.py from a user's

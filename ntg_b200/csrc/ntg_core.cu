@@ -113,6 +113,8 @@ struct ntgb_problem {
         cudaStream_t stream = nullptr;
     } hs[2];
     int *d_abort = nullptr; /* device flag: a callback wrote *mode = -1 */
+    /* scratch of ntgb_linesearch: trial coefficients, result table, linear violation */
+    struct { size_t n = 0; double *Ct = nullptr, *res = nullptr, *lv = nullptr; } ls;
 };
 
 namespace {
@@ -233,6 +235,50 @@ __global__ void k_spline_interp(InterpDesc D, int P, const double *C, int nt, co
     }
 }
 
+/* trial points of the line search: Ct[(p*nalpha + a)][.] = C[p][.] + alpha[a]*dC[p][.] */
+__global__ void k_ls_trial(const double *C, const double *dC, const double *alpha, int P, int nalpha, int nC,
+                           double *Ct)
+{
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)P * nalpha * nC;
+    if (q >= total) return;
+    const int e = (int)(q % nC);
+    const long long pa = q / nC;
+    const int a = (int)(pa % nalpha);
+    const long long p = pa / nalpha;
+    Ct[q] = C[p * nC + e] + alpha[a] * dC[p * nC + e];
+}
+
+/* per problem: first alpha satisfying Armijo on phi = f + mu*max(viol_nl, viol_lin), else argmin */
+__global__ void k_ls_pick(const double *res, const double *lv, const double *alpha, int P, int nalpha, double mu,
+                          double c1, const double *phi0, const double *dphi0, const double *C, const double *dC,
+                          int nC, double *alpha_best, double *phi_best, double *C_new)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    int best = 0, chosen = -1;
+    double phib = 0.0;
+    for (int a = 0; a < nalpha; a++) {
+        const size_t i = (size_t)p * nalpha + a;
+        double v = res[2 * i + 1];
+        if (lv != nullptr && lv[i] > v) v = lv[i];
+        const double phi = res[2 * i] + mu * v;
+        if (a == 0 || phi < phib) { phib = phi; best = a; }
+        if (chosen < 0 && phi0 != nullptr) {
+            const double slope = dphi0 != nullptr ? dphi0[p] : 0.0;
+            if (phi <= phi0[p] + c1 * alpha[a] * slope) chosen = a;
+        }
+    }
+    if (chosen < 0) chosen = best;
+    const size_t ic = (size_t)p * nalpha + chosen;
+    double v = res[2 * ic + 1];
+    if (lv != nullptr && lv[ic] > v) v = lv[ic];
+    if (alpha_best) alpha_best[p] = alpha[chosen];
+    if (phi_best) phi_best[p] = res[2 * ic] + mu * v;
+    if (C_new)
+        for (int e = 0; e < nC; e++) C_new[(size_t)p * nC + e] = C[(size_t)p * nC + e] + alpha[chosen] * dC[(size_t)p * nC + e];
+}
+
 int check_avs(const AV *av, int n, const ntgb_setup *s, const char *what)
 {
     if (n < 0 || (n > 0 && av == nullptr)) return fail(NTGB_EINVAL, "%s: bad active-variable list", what);
@@ -329,6 +375,9 @@ void ntgb_destroy(ntgb_problem *pb)
     if (!pb) return;
     DeviceGuard dg(pb->device);
     for (void *p : pb->allocs) cudaFree(p);
+    if (pb->ls.Ct) cudaFree(pb->ls.Ct);
+    if (pb->ls.res) cudaFree(pb->ls.res);
+    if (pb->ls.lv) cudaFree(pb->ls.lv);
     for (auto &h : pb->hs) {
         double *hsp[] = {h.C, h.f, h.g, h.c, h.J, h.Z, h.result};
         for (double *p : hsp)
@@ -838,6 +887,51 @@ int ntgb_eval_linear(ntgb_problem *pb, int P, const double *C, double *lin, doub
     const unsigned grid = (unsigned)((total + block - 1) / block);
     k_linear<<<grid, block, 0, st>>>(pb->dAband, pb->dAcol0, pb->dlin_lb, pb->dlin_ub, nclin, pb->dims.nout,
                                      pb->dims.sorder, pb->tab, P, C, lin, viol);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int ntgb_linesearch(ntgb_problem *pb, int P, const double *C, const double *dC, int nalpha, const double *alpha,
+                    double mu, double c1, const double *phi0, const double *dphi0, double *alpha_best,
+                    double *phi_best, double *C_new, void *stream)
+{
+    if (!pb || !C || !dC || !alpha) return fail(NTGB_EINVAL, "ntgb_linesearch: null argument");
+    if (P <= 0) return 0;
+    if (nalpha < 1 || nalpha > 64) return fail(NTGB_EINVAL, "nalpha = %d outside [1,64]", nalpha);
+    DeviceGuard dg(pb->device);
+    if (!dg.ok) return fail(NTGB_ECUDA, "cannot select device %d", pb->device);
+    const ntgb_dims &d = pb->dims;
+    const size_t n = (size_t)P * nalpha;
+    if (n > 0x7fffffffull) return fail(NTGB_EINVAL, "P*nalpha too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n > pb->ls.n) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (pb->ls.Ct) cudaFree(pb->ls.Ct);
+        if (pb->ls.res) cudaFree(pb->ls.res);
+        if (pb->ls.lv) cudaFree(pb->ls.lv);
+        pb->ls.Ct = pb->ls.res = pb->ls.lv = nullptr;
+        pb->ls.n = 0;
+        CUDA_TRY(cudaMalloc((void **)&pb->ls.Ct, n * d.nC * sizeof(double)));
+        CUDA_TRY(cudaMalloc((void **)&pb->ls.res, n * 2 * sizeof(double)));
+        CUDA_TRY(cudaMalloc((void **)&pb->ls.lv, n * sizeof(double)));
+        pb->ls.n = n;
+    }
+    const long long total = (long long)n * d.nC;
+    k_ls_trial<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(C, dC, alpha, P, nalpha, d.nC, pb->ls.Ct);
+    CUDA_TRY(cudaGetLastError());
+    ntgb_eval_args a;
+    memset(&a, 0, sizeof a);
+    a.P = (int)n; a.C = pb->ls.Ct; a.mode_obj = 0; a.mode_con = d.ncnln > 0 ? 0 : -1;
+    a.result = pb->ls.res; a.jac_layout = NTGB_JAC_NONE; a.stream = st;
+    int rc = ntgb_eval(pb, &a);
+    if (rc) return rc;
+    const bool lin = d.nclin > 0;
+    if (lin) {
+        rc = ntgb_eval_linear(pb, (int)n, pb->ls.Ct, nullptr, pb->ls.lv, st);
+        if (rc) return rc;
+    }
+    k_ls_pick<<<(unsigned)((P + 127) / 128), 128, 0, st>>>(pb->ls.res, lin ? pb->ls.lv : nullptr, alpha, P, nalpha, mu,
+                                                          c1, phi0, dphi0, C, dC, d.nC, alpha_best, phi_best, C_new);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

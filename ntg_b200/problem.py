@@ -48,6 +48,9 @@ def core() -> C.CDLL:
         lib.ntgb_get_linear.argtypes = [C.c_void_p, c_double_p]
         lib.ntgb_get_bounds.argtypes = [C.c_void_p, c_double_p, c_double_p]
         lib.ntgb_eval_linear.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.ntgb_linesearch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                        C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]
         lib.ntgb_spline_interp.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                            C.c_void_p, C.c_void_p]
         _core = lib
@@ -258,6 +261,19 @@ class Problem:
         st = torch.cuda.current_stream(Cdev.device).cuda_stream
         _check(core().ntgb_eval_linear(self._h, P, Cdev.data_ptr(), lin.data_ptr(), viol.data_ptr(), st))
         return lin[:, :d.nclin], viol
+
+    def linesearch(self, Cdev, dCdev, alphas, mu, c1=1e-4, phi0=None, dphi0=None):
+        """batched merit line search (ntgb_linesearch); returns alpha_best [P], phi_best [P], C_new"""
+        import torch
+        P = Cdev.shape[0]
+        ab = torch.zeros(P, dtype=torch.float64, device=Cdev.device)
+        pbest = torch.zeros(P, dtype=torch.float64, device=Cdev.device)
+        Cn = torch.zeros_like(Cdev)
+        st = torch.cuda.current_stream(Cdev.device).cuda_stream
+        _check(core().ntgb_linesearch(self._h, P, Cdev.data_ptr(), dCdev.data_ptr(), int(alphas.shape[0]),
+                                      alphas.data_ptr(), float(mu), float(c1), _ptr(phi0), _ptr(dphi0),
+                                      ab.data_ptr(), pbest.data_ptr(), Cn.data_ptr(), st))
+        return ab, pbest, Cn
 
     def spline_interp(self, Cdev, tdev):
         import torch

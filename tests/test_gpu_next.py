@@ -172,3 +172,42 @@ print("INFORM", inform.value)
     p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert "INFORM -1000" in p.stdout, p.stdout + p.stderr
     assert "NPSOL" in p.stderr
+
+
+@pytest.mark.parametrize("name", ["cfg3_kincar", "endpoint"])
+def test_batched_merit_linesearch(port, name):
+    """ntgb_linesearch: P*nalpha values-only evaluations in one launch + per-problem Armijo /
+    argmin selection, against the CPU oracle evaluated at the same trial points."""
+    import torch
+    from ntg_b200 import Problem
+    from common import violation
+    spec, X = golden_spec(name)
+    rng = np.random.default_rng(21)
+    P, nC = X.shape
+    D = rng.uniform(-1, 1, (P, nC))
+    alphas = np.array([1.0, 0.5, 0.25, 0.125, 0.0625])
+    mu, c1 = 3.0, 1e-4
+    o = port.eval(spec, X, dense=False, band=False, linear=True)
+    def merit(Xe):
+        r = port.eval(spec, Xe, mode_obj=0, mode_con=0, dense=False, band=False)
+        v = violation(spec, r["c"])
+        lin = Xe @ o["A"].T
+        lb, ub = o["bl"][nC:nC + spec.nclin], o["bu"][nC:nC + spec.nclin]
+        vl = np.maximum(np.maximum(lb - lin, lin - ub), 0).max(axis=1) if spec.nclin else np.zeros(len(Xe))
+        return r["f"] + mu * np.maximum(v, vl)
+    phi0 = merit(X)
+    dphi0 = -np.abs(rng.uniform(0.1, 1.0, P)) * np.abs(phi0)
+    trial = np.stack([merit(X + a * D) for a in alphas], axis=1)          # [P][nalpha]
+    want_a, want_phi = np.zeros(P), np.zeros(P)
+    for p in range(P):
+        ok = [i for i, a in enumerate(alphas) if trial[p, i] <= phi0[p] + c1 * a * dphi0[p]]
+        i = ok[0] if ok else int(np.argmin(trial[p]))
+        want_a[p], want_phi[p] = alphas[i], trial[p, i]
+    pb = Problem(spec, 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    ab, pbest, Cn = pb.linesearch(t(X), t(D), t(alphas), mu, c1, t(phi0), t(dphi0))
+    torch.cuda.synchronize()
+    assert_close(pbest.cpu().numpy(), want_phi, "merit at the chosen step")
+    assert np.array_equal(ab.cpu().numpy(), want_a), "chosen step sizes"
+    assert_bitexact(Cn.cpu().numpy(), X + want_a[:, None] * D, "updated coefficients")
+    pb.close()

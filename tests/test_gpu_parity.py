@@ -350,3 +350,42 @@ def test_callback_abort_request(torch_cuda):
         pb.eval_host(Xbad)
     pb.eval_host(X)              # and the next clean call succeeds again
     pb.close()
+
+
+@pytest.mark.parametrize("case", ["k1s_endpoint", "k1s_kincar64", "k1_endpoint", "k1_syn6", "k1c_301", "k1c_601"])
+@pytest.mark.parametrize("jac", [JAC_BAND, JAC_DENSE], ids=["band", "dense"])
+def test_no_out_of_bounds_writes(torch_cuda, case, jac, monkeypatch):
+    """compute-sanitizer is closed on this pool: every output lives inside a larger buffer of
+    sentinels; after a launch the guard zones on both sides must be untouched and the interior of
+    the fully-written outputs must hold no sentinel."""
+    torch = torch_cuda
+    from ntg_b200 import Problem
+    from ntg_b200.abi import NtgbEvalArgs
+    spec, P = {"k1s_endpoint": (configs.endpoint(), 7), "k1s_kincar64": (configs.kincar(64), 9),
+               "k1_endpoint": (configs.endpoint(), 7), "k1_syn6": (configs.syn6(12, name="s12"), 3),
+               "k1c_301": (configs.syn6(150, name="s150"), 3), "k1c_601": (configs.syn6(300, name="s300"), 2)}[case]
+    if case == "k1_endpoint":
+        monkeypatch.setenv("NTG_B200_KERNEL", "general")
+    if jac == JAC_DENSE and spec.ncnln * spec.nC * P > 4e7:
+        pytest.skip("dense Jacobian too large for this case")
+    pb = Problem(spec, 0)
+    d = pb.dims
+    PAD, S = 4096, -7.25e300
+    sizes = {"f": P, "g": P * d.nC, "c": P * d.ncnln, "result": P * 2, "Z": P * d.nZ,
+             "J": P * d.ncnln * (d.sorder if jac == JAC_BAND else d.nC)}
+    big = {k: torch.full((n + 2 * PAD,), S, dtype=torch.float64, device="cuda") for k, n in sizes.items()}
+    X = torch.from_numpy(np.random.default_rng(3).uniform(-1, 1, (P, spec.nC))).cuda()
+    a = NtgbEvalArgs()
+    a.P, a.C, a.mode_obj, a.mode_con, a.nstate = P, X.data_ptr(), 2, 2, 0
+    for k in ("f", "g", "c", "J", "Z", "result"):
+        setattr(a, k, big[k].data_ptr() + PAD * 8)
+    a.jac_layout = jac
+    a.stream = torch.cuda.current_stream().cuda_stream
+    pb.launch(a)
+    torch.cuda.synchronize()
+    for k, n in sizes.items():
+        b = big[k].cpu().numpy()
+        assert np.all(b[:PAD] == S) and np.all(b[PAD + n:] == S), f"{case}: wrote outside {k}"
+        if k != "J" or jac == JAC_BAND:
+            assert not np.any(b[PAD:PAD + n] == S), f"{case}: {k} not fully written"
+    pb.close()

@@ -405,6 +405,12 @@ int ntgb_create(ntgb_problem **out, const ntgb_setup *s, int device)
         if (s->mult[j] < 0 || s->mult[j] >= s->order[j])
             return fail(NTGB_EINVAL, "mult[%d] = %d outside [0,order)", j, s->mult[j]);
         if (s->kninterv[j] < 1 || !s->knots[j]) return fail(NTGB_EINVAL, "output %d: bad knots", j);
+        /* a breakpoint in front of the first knot is undefined in the reference (interv returns
+         * left = 1 and bsplvb reads t(left+1-j) before the knot array); refuse it */
+        for (int i = 0; i < s->nbps; i++)
+            if (s->bps[i] < s->knots[j][0])
+                return fail(NTGB_EINVAL, "breakpoint %d (%.17g) lies before the first knot of output %d (%.17g)", i,
+                            s->bps[i], j, s->knots[j][0]);
     }
     int rc;
     if ((rc = check_avs(s->initialcostav, s->ninitialcostav, s, "initialcostav"))) return rc;

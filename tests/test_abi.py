@@ -60,6 +60,11 @@ def test_argument_validation_happens_before_cuda(built_libs):
     rc, msg, _ = _create(spec, "vdp")
     assert rc == -1 and "order" in msg                      # NTGB_EINVAL: PGS limit order <= 20
     spec = configs.vanderpol()
+    spec.bps = spec.bps.copy()
+    spec.bps[3] = -0.25
+    rc, msg, _ = _create(spec, "vdp")
+    assert rc == -1 and "before the first knot" in msg
+    spec = configs.vanderpol()
     spec.trajectorycostav = [(0, 7)]
     rc, msg, _ = _create(spec, "vdp")
     assert rc == -1 and "trajectorycostav" in msg

@@ -269,7 +269,7 @@ def test_error_paths_on_gpu(torch_cuda):
     pb.close()
 
 
-def _random_spec(rng, family):
+def _random_spec(rng, family, unsorted=False):
     """Random spline setups around the packs' compile-time shapes: random order / mult /
     interval count, non-uniform knots, non-uniform breakpoints (first and last on the ends)."""
     import copy
@@ -297,16 +297,26 @@ def _random_spec(rng, family):
         spec.knots = [np.sort(np.concatenate([[0.0, 2.0], rng.uniform(0.0, 2.0, ni - 1)])) for ni in spec.ninterv]
         t1 = 2.0
     spec.bps = np.sort(np.concatenate([[0.0, t1], rng.uniform(0.0, t1, nbps - 2)])) if nbps > 2 else np.array([0.0, t1])
+    if unsorted and nbps > 4:
+        # the reference does not require ascending breakpoints: shuffle the interior, repeat one,
+        # put one past the last knot (extrapolated, like linspace's accumulated end point).  A
+        # breakpoint BEFORE the first knot is undefined in the reference itself: interv returns
+        # left = 1 and bsplvb then reads t(left+1-j) in front of the knot array.
+        inner = spec.bps[1:-1].copy()
+        rng.shuffle(inner)
+        inner[0] = inner[1]
+        inner[3] = t1 + 0.05
+        spec.bps = np.concatenate([[0.0], inner, [t1]])
     spec.nbps = nbps
     spec.name = f"random_{family}"
     return spec
 
 
-@pytest.mark.parametrize("seed", list(range(14)))
+@pytest.mark.parametrize("seed", list(range(22)))
 def test_random_shapes(torch_cuda, port, seed, monkeypatch):
     rng = np.random.default_rng(1000 + seed)
     family = "endpt" if seed % 2 == 0 else "kincar"
-    spec = _random_spec(rng, family)
+    spec = _random_spec(rng, family, unsorted=seed >= 14)
     if seed % 4 == 2:
         monkeypatch.setenv("NTG_B200_KERNEL", "general")
     P = int(rng.choice([1, 5, 37]))

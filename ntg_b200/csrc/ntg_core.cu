@@ -119,6 +119,18 @@ struct ntgb_problem {
 
 namespace {
 
+/* launch and return THIS launch's status (cudaGetLastError() could hand back a stale error that
+ * another library left on the thread) */
+template <class... KArgs, class... Args>
+cudaError_t launch(void (*kern)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.stream = st;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 template <class T>
 int dev_alloc(ntgb_problem *pb, T **ptr, size_t n)
 {
@@ -519,9 +531,9 @@ int ntgb_create(ntgb_problem **out, const ntgb_setup *s, int device)
         if ((rc = dev_alloc(pb, &dBt, (size_t)nbps * order * md))) return rc;
         if ((rc = dev_alloc(pb, &doff, (size_t)nbps))) return rc;
         if ((rc = dev_alloc(pb, &dleft, (size_t)nbps))) return rc;
-        k0_augknots<<<(naug + 127) / 128, 128>>>(dk, ni, order, mult, daug, naug);
-        k0_tables<<<(nbps + 63) / 64, 64>>>(daug, naug, dk, ni + 1, dbps, nbps, order, mult, md, dBn, dBt, doff, dleft);
-        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(launch(k0_augknots, (naug + 127) / 128, 128, nullptr, dk, ni, order, mult, daug, naug));
+        CUDA_TRY(launch(k0_tables, (nbps + 63) / 64, 64, nullptr, daug, naug, dk, ni + 1, dbps, nbps, order, mult, md,
+                        dBn, dBt, doff, dleft));
         T.Bn[j] = dBn; T.Bt[j] = dBt; T.off[j] = doff;
         pb->daug[j] = daug; pb->dknots[j] = dk;
         pb->augknots[j].resize(naug);
@@ -891,9 +903,8 @@ int ntgb_eval_linear(ntgb_problem *pb, int P, const double *C, double *lin, doub
     const long long total = (long long)P * nclin;
     const int block = 256;
     const unsigned grid = (unsigned)((total + block - 1) / block);
-    k_linear<<<grid, block, 0, st>>>(pb->dAband, pb->dAcol0, pb->dlin_lb, pb->dlin_ub, nclin, pb->dims.nout,
-                                     pb->dims.sorder, pb->tab, P, C, lin, viol);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch(k_linear, grid, block, st, pb->dAband, pb->dAcol0, pb->dlin_lb, pb->dlin_ub, nclin,
+                    pb->dims.nout, pb->dims.sorder, pb->tab, P, C, lin, viol));
     return 0;
 }
 
@@ -923,8 +934,7 @@ int ntgb_linesearch(ntgb_problem *pb, int P, const double *C, const double *dC, 
         pb->ls.n = n;
     }
     const long long total = (long long)n * d.nC;
-    k_ls_trial<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(C, dC, alpha, P, nalpha, d.nC, pb->ls.Ct);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch(k_ls_trial, (unsigned)((total + 255) / 256), 256, st, C, dC, alpha, P, nalpha, d.nC, pb->ls.Ct));
     ntgb_eval_args a;
     memset(&a, 0, sizeof a);
     a.P = (int)n; a.C = pb->ls.Ct; a.mode_obj = 0; a.mode_con = d.ncnln > 0 ? 0 : -1;
@@ -936,9 +946,8 @@ int ntgb_linesearch(ntgb_problem *pb, int P, const double *C, const double *dC, 
         rc = ntgb_eval_linear(pb, (int)n, pb->ls.Ct, nullptr, pb->ls.lv, st);
         if (rc) return rc;
     }
-    k_ls_pick<<<(unsigned)((P + 127) / 128), 128, 0, st>>>(pb->ls.res, lin ? pb->ls.lv : nullptr, alpha, P, nalpha, mu,
-                                                          c1, phi0, dphi0, C, dC, d.nC, alpha_best, phi_best, C_new);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch(k_ls_pick, (unsigned)((P + 127) / 128), 128, st, pb->ls.res, lin ? pb->ls.lv : nullptr, alpha, P,
+                    nalpha, mu, c1, phi0, dphi0, C, dC, d.nC, alpha_best, phi_best, C_new));
     return 0;
 }
 
@@ -958,8 +967,8 @@ int ntgb_spline_interp(ntgb_problem *pb, int P, const double *C, int nt, const d
     }
     const long long total = (long long)P * nt * D.nout;
     const int block = 128;
-    k_spline_interp<<<(unsigned)((total + block - 1) / block), block, 0, (cudaStream_t)stream>>>(D, P, C, nt, t, out);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch(k_spline_interp, (unsigned)((total + block - 1) / block), block, (cudaStream_t)stream, D, P, C, nt,
+                    t, out));
     return 0;
 }
 

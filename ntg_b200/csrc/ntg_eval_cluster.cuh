@@ -523,7 +523,7 @@ int launch_eval_cluster(const ntgb_launch *L)
         const size_t smem = lay.bytes();
         if (smem > (size_t)L->max_smem_optin) return -1001;
         auto kern = full ? ntg_eval_cluster_kernel<PK, true> : ntg_eval_cluster_kernel<PK, false>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = raise_smem_limit((const void *)kern, L->max_smem_optin);
         if (e != cudaSuccess) return (int)e;
         int nclusters = L->sm_count / CL;
         if (nclusters > P) nclusters = P;
@@ -540,9 +540,7 @@ int launch_eval_cluster(const ntgb_launch *L)
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, kern, T, L->args, CL, bpc, T.plan_cwin, plan_smem);
-        if (e != cudaSuccess) return (int)e;
-        return (int)cudaGetLastError();
+        return (int)cudaLaunchKernelEx(&cfg, kern, T, L->args, CL, bpc, T.plan_cwin, plan_smem);
     }
 }
 

@@ -456,6 +456,50 @@ __global__ void __launch_bounds__(256) ntg_eval_kernel(const ntgb_devtab T, cons
 }
 
 /* ------------------------------ host launcher ------------------------------ */
+
+/* Per-launch host work matters for the small configs (a 4096-problem batch is ~5 us of GPU time):
+ * the shared-memory opt-in and the occupancy query are done once per (kernel, device, block, smem). */
+struct LaunchPlanCache {
+    struct Entry { const void *kern; int dev, block; size_t smem; int nb; };
+    Entry e[16];
+    int n = 0;
+};
+/* raise the kernel's dynamic shared-memory limit to everything the device offers beyond the
+ * kernel's own static shared memory */
+inline cudaError_t raise_smem_limit(const void *kern, int max_optin)
+{
+    cudaFuncAttributes fa;
+    cudaError_t err = cudaFuncGetAttributes(&fa, kern);
+    if (err != cudaSuccess) return err;
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - (int)fa.sharedSizeBytes);
+}
+
+inline int resident_blocks(const void *kern, int block, size_t smem, int max_optin, int *nb_out)
+{
+    static thread_local LaunchPlanCache cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    for (int i = 0; i < cache.n; i++)
+        if (cache.e[i].kern == kern && cache.e[i].dev == dev && cache.e[i].block == block && cache.e[i].smem == smem) {
+            *nb_out = cache.e[i].nb;
+            return 0;
+        }
+    cudaError_t err;
+    if (smem > 48 * 1024) {
+        /* the attribute is a LIMIT that a later, smaller value would lower again (a cached larger
+         * configuration would then fail to launch): raise it once to the device maximum */
+        err = raise_smem_limit(kern, max_optin);
+        if (err != cudaSuccess) return (int)err;
+    }
+    int nb = 0;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, block, smem);
+    if (err != cudaSuccess) return (int)err;
+    if (nb < 1) nb = 1;
+    if (cache.n < 16) cache.e[cache.n++] = {kern, dev, block, smem, nb};
+    *nb_out = nb;
+    return 0;
+}
+
 template <class PK>
 int launch_eval(const ntgb_launch *L)
 {
@@ -480,21 +524,20 @@ int launch_eval(const ntgb_launch *L)
     const size_t smem = lay.doubles() * sizeof(double);
     if (smem > (size_t)L->max_smem_optin) return -1000; /* caller reports NTGB_ELIMIT */
     auto kern = ntg_eval_kernel<PK>;
-    cudaError_t e;
-    if (smem > 48 * 1024) {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-    }
     int nb = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, block, smem);
-    if (e != cudaSuccess) return (int)e;
-    if (nb < 1) nb = 1;
+    if (int rc = resident_blocks((const void *)kern, block, smem, L->max_smem_optin, &nb)) return rc;
     const int ntiles = (L->args.P + G - 1) / G;
     int grid = nb * L->sm_count;
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) return 0;
-    kern<<<grid, block, smem, (cudaStream_t)L->args.stream>>>(T, L->args, G);
-    return (int)cudaGetLastError();
+    /* cudaLaunchKernelEx reports THIS launch's status; cudaGetLastError() would also return a stale
+     * error some other library left behind on this thread */
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)L->args.stream;
+    return (int)cudaLaunchKernelEx(&cfg, kern, T, L->args, G);
 }
 
 } /* namespace ntgb */

@@ -29,6 +29,7 @@
 #ifndef NTG_EVAL_SMALL_CUH_
 #define NTG_EVAL_SMALL_CUH_
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -550,21 +551,22 @@ int launch_eval_small(const ntgb_launch *L)
     const size_t smem = lay.bytes();
     if (smem > (size_t)L->max_smem_optin) return -1001;
     auto kern = full ? ntg_eval_small_kernel<PK, true> : ntg_eval_small_kernel<PK, false>;
-    cudaError_t e;
-    if (smem > 48 * 1024) {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-    }
     int nb = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, block, smem);
-    if (e != cudaSuccess) return (int)e;
-    if (nb < 1) nb = 1;
+    if (int rc = resident_blocks((const void *)kern, block, smem, L->max_smem_optin, &nb)) return rc;
     const int ntiles = (P + G * R - 1) / (G * R);
     int grid = nb * L->sm_count;
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) return 0;
-    kern<<<grid, block, smem, (cudaStream_t)L->args.stream>>>(T, L->args, G, R, segtot);
-    return (int)cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)L->args.stream;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, T, L->args, G, R, segtot);
+    if (le != cudaSuccess && getenv("NTG_B200_DEBUG"))
+        fprintf(stderr, "K1s launch failed: grid %d block %d smem %zu G %d R %d P %d nb %d: %s\n", grid, block, smem, G,
+                R, P, nb, cudaGetErrorString(le));
+    return (int)le;
 }
 
 } /* namespace ntgb */

@@ -399,3 +399,23 @@ def test_no_out_of_bounds_writes(torch_cuda, case, jac, monkeypatch):
         if k != "J" or jac == JAC_BAND:
             assert not np.any(b[PAD:PAD + n] == S), f"{case}: {k} not fully written"
     pb.close()
+
+
+def test_alternating_batch_sizes_keep_launching(torch_cuda, port):
+    """Regression: the shared-memory opt-in is a per-kernel LIMIT; alternating between batch sizes
+    that need more and less dynamic shared memory (what ntgb_eval_host's chunking does) must not
+    lower it under a configuration that is used again."""
+    spec, _ = configs.get("cfg4")
+    from ntg_b200 import Problem
+    import torch
+    pb = Problem(spec, 0, fast=True)
+    X = configs.coefficients("cfg4", 70000, spec)
+    ref = port.eval(spec, X[:64], dense=False, band=False)
+    for P in (65536, 5829, 1417, 5829, 65536, 300, 65536):
+        o = pb.eval(torch.from_numpy(X[:P]).cuda())
+        torch.cuda.synchronize()
+        assert_close(o["f"][:64].cpu().numpy(), ref["f"], f"P={P}")
+    h = pb.eval_host(X[:20000])
+    h = pb.eval_host(X[:20000])
+    assert_close(h["f"][:64], ref["f"], "chunked host path, second call")
+    pb.close()

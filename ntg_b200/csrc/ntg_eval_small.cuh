@@ -544,6 +544,7 @@ int launch_eval_small(const ntgb_launch *L)
     int R = (block + G * (T.nC + 1) - 1) / (G * (T.nC + 1));
     const int r_wave = (int)(((long long)P + (long long)G * slots - 1) / ((long long)G * slots));
     if (r_wave <= 8) R = r_wave;   /* single wave */
+    if (const char *er = getenv("NTG_B200_ROUNDS")) R = atoi(er); /* tuning experiments */
     if (R < 1) R = 1;
     if (R > 8) R = 8;
     while (R > 1 && SmallSmem{G * R, nbps, T.S, T.nout, T.nC, segtot}.bytes() > 100 * 1024) R--;

@@ -162,7 +162,7 @@ def cpu_baseline(cfg: str, target_seconds: float = 4.0):
     try:
         n = ref.sample_size(target_seconds)
         ref.step(min(n, ref.cores * 2))  # warm the workers (imports, table build)
-        wall, inner = ref.step(n)
+        wall, inner = min((ref.step(n) for _ in range(3)), key=lambda t: t[1])  # best of 3 passes
         one = CpuReference(cfg, cores=1)
         n1 = max(1, n // ref.cores)
         one.step(1)

@@ -419,3 +419,33 @@ def test_alternating_batch_sizes_keep_launching(torch_cuda, port):
     h = pb.eval_host(X[:20000])
     assert_close(h["f"][:64], ref["f"], "chunked host path, second call")
     pb.close()
+
+
+def test_cfg5_full_batch_properties(torch_cuda, port):
+    """BASELINE.json's synthetic config at its full size on one GPU (16384 problems, 6 outputs,
+    order 8, 401 breakpoints: 11.6 GB of results): a slice evaluated on its own is bit-identical to
+    the same rows of the full batch, eight scattered problems match the CPU oracle bit for bit
+    (exact variant), and the (objective, violation) table agrees with f and c."""
+    torch = torch_cuda
+    from ntg_b200 import Problem
+    spec, P = configs.get("cfg5")
+    Xh = configs.coefficients("cfg5", P, spec)
+    X = torch.from_numpy(Xh).cuda()
+    pb = Problem(spec, 0, fast=False)
+    a = pb.eval(X)
+    lo, hi = 9000, 9000 + 77
+    b = pb.eval(X[lo:hi].contiguous())
+    for k in ("f", "g", "c", "J", "result"):
+        assert torch.equal(b[k], a[k][lo:hi]), f"{k}: depends on batch slicing"
+    pick = np.array([0, 1, 4095, 8191, 9001, 12345, 16000, 16383])
+    o = port.eval(spec, Xh[pick], dense=False, band=True)
+    idx = torch.from_numpy(pick).cuda()
+    assert_bitexact(a["f"][idx].cpu().numpy(), o["f"], "f")
+    assert_bitexact(a["g"][idx].cpu().numpy(), o["g"], "g")
+    assert_bitexact(a["c"][idx].cpu().numpy()[:, :spec.ncnln], o["c"], "c")
+    assert_bitexact(pb.band_to_rows(a["J"][idx].cpu().numpy()), o["Jband"], "J")
+    assert torch.equal(a["result"][:, 0], a["f"])
+    assert_close(a["result"][idx, 1].cpu().numpy(), violation(spec, o["c"]), "violation")
+    del a, b
+    torch.cuda.empty_cache()
+    pb.close()

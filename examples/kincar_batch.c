@@ -58,12 +58,17 @@ int main(int argc, char **argv)
         fprintf(stderr, "unexpected sizes %d %d %d\n", d.nC, d.ncnln, d.sorder);
         return 3;
     }
-    C = malloc(sizeof(double) * (size_t)P * NC);
-    f = malloc(sizeof(double) * (size_t)P);
-    g = malloc(sizeof(double) * (size_t)P * NC);
-    c = malloc(sizeof(double) * (size_t)P * NCNLN);
-    J = malloc(sizeof(double) * (size_t)P * NCNLN * S);
-    res = malloc(sizeof(double) * (size_t)P * 2);
+    /* page-locked buffers: ntgb_eval_host then overlaps its copies with the kernels */
+    C = ntgb_host_alloc(sizeof(double) * (size_t)P * NC);
+    f = ntgb_host_alloc(sizeof(double) * (size_t)P);
+    g = ntgb_host_alloc(sizeof(double) * (size_t)P * NC);
+    c = ntgb_host_alloc(sizeof(double) * (size_t)P * NCNLN);
+    J = ntgb_host_alloc(sizeof(double) * (size_t)P * NCNLN * S);
+    res = ntgb_host_alloc(sizeof(double) * (size_t)P * 2);
+    if (!C || !f || !g || !c || !J || !res) {
+        fprintf(stderr, "host allocation: %s\n", ntgb_last_error());
+        return 5;
+    }
     for (p = 0; p < P; p++)
         for (e = 0; e < NC; e++) { /* a reproducible batch: x coefficients in [0,40), y in [-2,2) */
             double u;
@@ -81,6 +86,6 @@ int main(int argc, char **argv)
         printf("p %d f %.17g g0 %.17g c0 %.17g J0 %.17g viol %.17g\n", p, f[p], g[(size_t)p * NC],
                c[(size_t)p * NCNLN], J[(size_t)p * NCNLN * S], res[2 * p + 1]);
     ntgb_destroy(pb);
-    free(C); free(f); free(g); free(c); free(J); free(res);
+    ntgb_host_free(C); ntgb_host_free(f); ntgb_host_free(g); ntgb_host_free(c); ntgb_host_free(J); ntgb_host_free(res);
     return 0;
 }

@@ -17,6 +17,8 @@
 #ifndef NTG_B200_H_
 #define NTG_B200_H_
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -155,6 +157,14 @@ int  ntgb_eval(ntgb_problem *pb, const ntgb_eval_args *args);
 /* same call with HOST buffers: H2D of C, launch, D2H of the requested outputs,
  * synchronous.  This is what ntg()'s funobj/funcon trampolines use. */
 int  ntgb_eval_host(ntgb_problem *pb, const ntgb_eval_args *host_args);
+
+/* Page-locked host memory for ntgb_eval_host (so its copies are asynchronous and overlap the
+ * kernels) without pulling CUDA headers into a C program; ntgb_host_register pins memory the
+ * caller already owns. */
+void *ntgb_host_alloc(size_t bytes);
+void  ntgb_host_free(void *p);
+int   ntgb_host_register(void *p, size_t bytes);
+int   ntgb_host_unregister(void *p);
 
 /*
  * One-time tables built on the device by K0 (replaces CollocMatrix + PGS,

@@ -891,6 +891,35 @@ int ntgb_eval_host(ntgb_problem *pb, const ntgb_eval_args *h)
     return 0;
 }
 
+void *ntgb_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        fail(NTGB_ENOMEM, "cudaMallocHost(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+
+void ntgb_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+int ntgb_host_register(void *p, size_t bytes)
+{
+    if (!p) return fail(NTGB_EINVAL, "ntgb_host_register: null pointer");
+    CUDA_TRY(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+    return 0;
+}
+
+int ntgb_host_unregister(void *p)
+{
+    if (!p) return fail(NTGB_EINVAL, "ntgb_host_unregister: null pointer");
+    CUDA_TRY(cudaHostUnregister(p));
+    return 0;
+}
+
 int ntgb_eval_linear(ntgb_problem *pb, int P, const double *C, double *lin, double *viol, void *stream)
 {
     if (!pb || !C) return fail(NTGB_EINVAL, "ntgb_eval_linear: null argument");

@@ -93,6 +93,15 @@ def endpoint(nbps: int = 13, name: str = "test_endpoint") -> ProblemSpec:
         lic=lic, ltc=ltc, lfc=lfc, lowerb=lower, upperb=upper)
 
 
+def high_order(order: int = 20, mult: int = 3, ninterv: int = 4, nbps: int = 33, name: str = "test_hi20") -> ProblemSpec:
+    """Test-only: the upper limit of the spline machinery (order 20 = PGS bsplvb's jmax)."""
+    av = [(0, 0), (0, 1), (0, 2)]
+    return ProblemSpec(
+        name=name, pack="hi20", order=[order], mult=[mult], maxderiv=[3], ninterv=[ninterv], nbps=nbps,
+        t0=0.0, t1=1.0, callbacks={"ucf": "hi20_ucf", "nltcf": "hi20_nltcf"}, nucf=1, nnltc=1,
+        trajectorycostav=av, trajectoryconstrav=av, lowerb=np.array([-1.0]), upperb=np.array([1.0]))
+
+
 # BASELINE.json configs -> (spec factory, batch size, coefficient sampler)
 def coefficients(cfg: str, P: int, spec: ProblemSpec, seed: int | None = None) -> np.ndarray:
     """Synthetic coefficient batches, seeds and ranges of SURVEY.md section 8(d)."""

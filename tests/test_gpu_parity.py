@@ -449,3 +449,35 @@ def test_cfg5_full_batch_properties(torch_cuda, port):
     del a, b
     torch.cuda.empty_cache()
     pb.close()
+
+
+@pytest.mark.parametrize("order,mult,ninterv,nbps,P", [(20, 3, 4, 33, 9), (20, 19, 7, 64, 5), (12, 5, 3, 300, 3), (1 + 2, 0, 5, 9, 4)])
+def test_order_limits(torch_cuda, port, order, mult, ninterv, nbps, P):
+    """Maximum sizes: order 20 is PGS bsplvb's limit (jmax = 20); also
+    multiplicity order-1 (smoothest), multiplicity 0, and a long horizon on the general kernel."""
+    spec = configs.high_order(order, mult, ninterv, nbps)
+    X = np.random.default_rng(order * 100 + mult).uniform(-1, 1, (P, spec.nC))
+    o = port.eval(spec, X, dense=False, band=True)
+    pb, r = gpu_eval(torch_cuda, spec, X, False)
+    B, off, _ = pb.tables()
+    Bo, offo, _ = port.tables(spec)
+    assert_bitexact(B[0], Bo[0], "K0 table at the order limit")
+    assert_bitexact(off, offo, "offsets")
+    for k in ("f", "g", "c", "Jband"):
+        assert_bitexact(r[k], o[k], f"order {order} mult {mult}: {k}")
+    pb.close()
+
+
+def test_empty_batch_is_a_no_op(torch_cuda):
+    import torch
+    from ntg_b200 import Problem
+    spec, _ = configs.get("cfg2")
+    pb = Problem(spec, 0)
+    X = torch.zeros((0, spec.nC), dtype=torch.float64, device="cuda")
+    out = pb.alloc_outputs(1)
+    a = pb.eval_args(torch.zeros((1, spec.nC), dtype=torch.float64, device="cuda"), out)
+    a.P = 0
+    pb.launch(a)
+    torch.cuda.synchronize()
+    assert float(out["f"].abs().sum()) == 0.0
+    pb.close()

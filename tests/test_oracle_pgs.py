@@ -83,6 +83,8 @@ SHAPES = {
     "kincar64": lambda: configs.kincar(64),
     "syn6_small": lambda: configs.syn6(12, name="syn6_small"),
     "endpoint": lambda: configs.endpoint(),
+    "order20": lambda: configs.high_order(20, 3, 3, 17),   # PGS limit: bsplvb jmax = 20
+    "order20_mult19": lambda: configs.high_order(20, 19, 5, 23),
 }
 
 

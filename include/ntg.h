@@ -42,8 +42,13 @@ typedef struct MatrixStruct {
  * Same 40 arguments, same order and meaning as reference src/ntg.h:72-99.
  * initialguess is overwritten with the solution (src/ntg.c:109).  Solving
  * needs NPSOL's npsol_/npoptn_ to be present in the process (they are looked
- * up at run time; NPSOL is separately licensed and never bundled): if they
- * are absent *inform is set to NTG_INFORM_NO_NPSOL and nothing is solved.
+ * up at run time; NPSOL is separately licensed and never bundled).  If they
+ * are absent, a problem with no nonlinear constraints and only equality linear
+ * constraints (the class of both shipped examples) is solved by the library's
+ * own reduced-space BFGS (ntgb_solve_eq; *inform = 0 / 1 / 4 with NPSOL's
+ * meaning, istate / clambda / R untouched, a notice on stderr; switch off with
+ * NTG_B200_NO_BUILTIN_SOLVER=1); for any other problem *inform is set to
+ * NTG_INFORM_NO_NPSOL and nothing is solved.
  */
 void ntg(int nout, double *bps, int nbps, int *kninterv, double **knots,
          int *order, int *mult, int *max_deriv,

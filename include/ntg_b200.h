@@ -213,6 +213,28 @@ int  ntgb_linesearch(ntgb_problem *pb, int P, const double *C, const double *dC,
                      const double *alpha, double mu, double c1, const double *phi0, const double *dphi0,
                      double *alpha_best, double *phi_best, double *C_new, void *stream);
 
+/*
+ * Batched solve for the class of problems both shipped examples belong to: no nonlinear
+ * constraints and only EQUALITY linear constraints (examples/vanderpol.c:159-169,
+ * examples/kincar.c:322-339).  Second step towards a batched SQP consumer (SURVEY.md
+ * section 8(f) rank 3): every problem of the batch is minimised independently, entirely on the
+ * GPU, by a reduced-space BFGS -- the linear constraints A*C = b are eliminated once on the host
+ * (C = C_part + N*y with N an orthonormal null-space basis of A), each iteration is one batched
+ * evaluation (cost + gradient), one tiny per-problem BFGS kernel and one batched Armijo line
+ * search (ntgb_linesearch).  C [P][nC] (device) holds the initial guesses on entry and the
+ * solutions on return; f [P], iters [P], status [P] (device, may be NULL) receive the final cost,
+ * the iteration count and 1 = reduced gradient below gtol, 2 = no further decrease, 0 = max_iter.
+ * Synchronous.  NTGB_EINVAL if the problem has nonlinear or inequality constraints.
+ */
+typedef struct ntgb_solve_opts {
+    int max_iter;     /* default 200 */
+    double gtol;      /* |reduced gradient|_inf <= gtol * max(1, |f|), default 1e-9 */
+    double c1;        /* Armijo constant, default 1e-4 */
+    int check_every;  /* host looks at the convergence counter every this many iterations, default 4 */
+} ntgb_solve_opts;
+int  ntgb_solve_eq(ntgb_problem *pb, int P, double *C, double *f, int *iters, int *status,
+                   const ntgb_solve_opts *opts, void *stream);
+
 /* ---- callback packs ------------------------------------------------------ */
 /*
  * A pack is a shared object produced by tools/ntg_pack.py from a user's

@@ -77,6 +77,11 @@ class NtgbEvalArgs(C.Structure):
     ]
 
 
+class SolveOpts(C.Structure):
+    """ntgb_solve_opts (include/ntg_b200.h)"""
+    _fields_ = [("max_iter", C.c_int), ("gtol", C.c_double), ("c1", C.c_double), ("check_every", C.c_int)]
+
+
 class NtgbPack(C.Structure):
     _fields_ = [
         ("name", C.c_char_p),

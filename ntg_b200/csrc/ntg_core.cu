@@ -16,7 +16,9 @@
  */
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cfloat>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -113,6 +115,16 @@ struct ntgb_problem {
         cudaStream_t stream = nullptr;
     } hs[2];
     int *d_abort = nullptr; /* device flag: a callback wrote *mode = -1 */
+    std::vector<double> lin_lb, lin_ub; /* expanded linear bounds, [nclin] */
+    /* reduced-space data of ntgb_solve_eq: C = C_part + N*y */
+    struct {
+        bool ready = false;
+        int nr = 0;
+        double *N = nullptr, *Cpart = nullptr; /* device: N [nr][nC] (basis vector k contiguous), Cpart [nC] */
+        int cap = 0;                           /* problems the per-problem scratch below holds */
+        double *blob = nullptr;
+        int *iblob = nullptr;
+    } red;
     /* scratch of ntgb_linesearch: trial coefficients, result table, linear violation */
     struct { size_t n = 0; double *Ct = nullptr, *res = nullptr, *lv = nullptr; } ls;
 };
@@ -291,6 +303,235 @@ __global__ void k_ls_pick(const double *res, const double *lv, const double *alp
         for (int e = 0; e < nC; e++) C_new[(size_t)p * nC + e] = C[(size_t)p * nC + e] + alpha[chosen] * dC[(size_t)p * nC + e];
 }
 
+/* ---- ntgb_solve_eq: reduced-space BFGS, one thread per problem ------------------------------
+ * Per-problem vectors are stored component-major ([k][P]) so that a warp's accesses coalesce. */
+constexpr int kSolveMaxNr = 32;
+
+__global__ void k_solve_init(int P, int nC, int nr, const double *N, const double *Cpart, double *C, double *y,
+                             double *H, int *state, int *iters, int *fails)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    double *Cp = C + (size_t)p * nC;
+    for (int k = 0; k < nr; k++) {
+        double a = 0.0;
+        for (int e = 0; e < nC; e++) a += N[(size_t)k * nC + e] * (Cp[e] - Cpart[e]);
+        y[(size_t)k * P + p] = a;
+    }
+    for (int e = 0; e < nC; e++) {
+        double a = Cpart[e];
+        for (int k = 0; k < nr; k++) a += N[(size_t)k * nC + e] * y[(size_t)k * P + p];
+        Cp[e] = a;
+    }
+    for (int k = 0; k < nr; k++)
+        for (int l = 0; l < nr; l++) H[((size_t)k * nr + l) * P + p] = k == l ? 1.0 : 0.0;
+    state[p] = 0;
+    iters[p] = 0;
+    fails[p] = -1; /* -1 no previous step, 1 last step failed (both: H = I, steepest descent);
+                      2 previous step exists and H is still the identity; 0 normal */
+}
+
+/* reduced gradient, convergence test, BFGS update of the inverse Hessian, search direction */
+__global__ void k_solve_dir(int P, int nC, int nr, const double *N, const double *f, const double *g, double gtol,
+                            const double *y, double *yp, double *grp, double *H, double *d, double *dC,
+                            double *phi0, double *dphi0, int *state, int *fails, int *count)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    double *dCp = dC + (size_t)p * nC;
+    phi0[p] = f[p];
+    if (state[p] != 0) {
+        for (int e = 0; e < nC; e++) dCp[e] = 0.0;
+        dphi0[p] = 0.0;
+        return;
+    }
+    double gr[kSolveMaxNr], s[kSolveMaxNr], u[kSolveMaxNr];
+    const double *gp = g + (size_t)p * nC;
+    double gmax = 0.0, gg = 0.0;
+    for (int k = 0; k < nr; k++) {
+        double a = 0.0;
+        for (int e = 0; e < nC; e++) a += N[(size_t)k * nC + e] * gp[e];
+        gr[k] = a;
+        gmax = fmax(gmax, fabs(a));
+        gg += a * a;
+    }
+    const double fabsv = fabs(f[p]);
+    if (!(gmax > gtol * (fabsv > 1.0 ? fabsv : 1.0))) {
+        /* converged (or NaN: nothing sensible left to do) */
+        state[p] = gmax == gmax ? 1 : 2;
+        atomicAdd(count, 1);
+        for (int e = 0; e < nC; e++) dCp[e] = 0.0;
+        dphi0[p] = 0.0;
+        return;
+    }
+#define HH(k, l) H[((size_t)(k) * nr + (l)) * P + p]
+    int fl = fails[p];
+    if (fl == 0 || fl == 2) {
+        /* s = y - y_prev, u = gr - gr_prev */
+        double su = 0.0, ss = 0.0, uu = 0.0;
+        for (int k = 0; k < nr; k++) {
+            s[k] = y[(size_t)k * P + p] - yp[(size_t)k * P + p];
+            u[k] = gr[k] - grp[(size_t)k * P + p];
+            su += s[k] * u[k]; ss += s[k] * s[k]; uu += u[k] * u[k];
+        }
+        if (su > 1e-10 * sqrt(ss * uu) && su > 0.0) {
+            if (fl == 2) /* first update after a (re)start: scale the identity to the curvature seen */
+                for (int k = 0; k < nr; k++) HH(k, k) = su / uu;
+            double Hu[kSolveMaxNr], uHu = 0.0;
+            for (int k = 0; k < nr; k++) {
+                double a = 0.0;
+                for (int l = 0; l < nr; l++) a += HH(k, l) * u[l];
+                Hu[k] = a;
+                uHu += a * u[k];
+            }
+            const double rho = 1.0 / su, c2 = (su + uHu) * rho * rho;
+            for (int k = 0; k < nr; k++)
+                for (int l = 0; l < nr; l++)
+                    HH(k, l) += c2 * s[k] * s[l] - rho * (Hu[k] * s[l] + s[k] * Hu[l]);
+        }
+    }
+    double slope = 0.0, dd = 0.0;
+    for (int k = 0; k < nr; k++) {
+        double a = 0.0;
+        for (int l = 0; l < nr; l++) a -= HH(k, l) * gr[l];
+        s[k] = a;
+        slope += a * gr[k];
+        dd += a * a;
+    }
+    if (!(slope < -1e-12 * sqrt(gg * dd))) {
+        /* not a descent direction: restart from steepest descent */
+        for (int k = 0; k < nr; k++)
+            for (int l = 0; l < nr; l++) HH(k, l) = k == l ? 1.0 : 0.0;
+        for (int k = 0; k < nr; k++) s[k] = -gr[k];
+        slope = -gg;
+        dd = gg;
+        fl = 1;
+        fails[p] = 1;
+    }
+#undef HH
+    /* a unit step along a raw gradient can be far too long: bound the first trial step */
+    const double dn = sqrt(dd);
+    const bool steepest = fl == -1 || fl == 1;
+    const double scale = (steepest && dn > 1.0) ? 1.0 / dn : 1.0;
+    if (fl == 2) fails[p] = 0;
+    for (int k = 0; k < nr; k++) {
+        s[k] *= scale;
+        d[(size_t)k * P + p] = s[k];
+        yp[(size_t)k * P + p] = y[(size_t)k * P + p];
+        grp[(size_t)k * P + p] = gr[k];
+    }
+    for (int e = 0; e < nC; e++) {
+        double a = 0.0;
+        for (int k = 0; k < nr; k++) a += N[(size_t)k * nC + e] * s[k];
+        dCp[e] = a;
+    }
+    dphi0[p] = slope * scale;
+}
+
+/* accept the line-search step (or count a failure), rebuild C from the reduced variables */
+__global__ void k_solve_update(int P, int nC, int nr, const double *N, const double *Cpart, const double *phi0,
+                               const double *alpha_best, const double *phi_best, const double *d, double *y,
+                               double *H, double *C, int *state, int *iters, int *fails, int *count)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P || state[p] != 0) return;
+    iters[p] += 1;
+    if (!(phi_best[p] < phi0[p])) {
+        /* no decrease along d: retry once from steepest descent, then give up */
+        const bool was_reset = fails[p] == -1 || fails[p] == 1;
+        if (was_reset) { state[p] = 2; atomicAdd(count, 1); return; }
+        for (int k = 0; k < nr; k++)
+            for (int l = 0; l < nr; l++) H[((size_t)k * nr + l) * P + p] = k == l ? 1.0 : 0.0;
+        fails[p] = 1;
+        return;
+    }
+    fails[p] = (fails[p] == -1 || fails[p] == 1) ? 2 : 0;
+    const double a = alpha_best[p];
+    for (int k = 0; k < nr; k++) y[(size_t)k * P + p] += a * d[(size_t)k * P + p];
+    double *Cp = C + (size_t)p * nC;
+    for (int e = 0; e < nC; e++) {
+        double v = Cpart[e];
+        for (int k = 0; k < nr; k++) v += N[(size_t)k * nC + e] * y[(size_t)k * P + p];
+        Cp[e] = v;
+    }
+}
+
+/* Host: orthonormal null-space basis N of A (m x n, column-major) and the minimum-norm solution of
+ * A*C = b, by Householder QR with column pivoting of A^T. */
+int reduce_linear(const std::vector<double> &A, int m, int n, const std::vector<double> &b, std::vector<double> &N,
+                  std::vector<double> &Cpart, int &nr)
+{
+    std::vector<double> M((size_t)n * std::max(m, 1)), Q((size_t)n * n, 0.0), v(n);
+    std::vector<int> perm(m);
+    for (int j = 0; j < m; j++) {
+        perm[j] = j;
+        for (int i = 0; i < n; i++) M[i + (size_t)j * n] = A[j + (size_t)i * m];
+    }
+    for (int i = 0; i < n; i++) Q[i + (size_t)i * n] = 1.0;
+    int r = 0;
+    double norm0 = 0.0;
+    for (int k = 0; k < std::min(n, m); k++) {
+        int jb = k;
+        double nb = -1.0;
+        for (int j = k; j < m; j++) {
+            double a = 0.0;
+            for (int i = k; i < n; i++) a += M[i + (size_t)j * n] * M[i + (size_t)j * n];
+            if (a > nb) { nb = a; jb = j; }
+        }
+        const double norm = std::sqrt(nb);
+        if (k == 0) norm0 = norm;
+        if (!(norm > 1e-11 * std::max(norm0, 1e-300))) break;
+        if (jb != k) {
+            for (int i = 0; i < n; i++) std::swap(M[i + (size_t)k * n], M[i + (size_t)jb * n]);
+            std::swap(perm[k], perm[jb]);
+        }
+        double *col = &M[(size_t)k * n];
+        const double alpha = col[k] > 0.0 ? -norm : norm;
+        double vv = 0.0;
+        for (int i = k; i < n; i++) { v[i] = col[i]; }
+        v[k] -= alpha;
+        for (int i = k; i < n; i++) vv += v[i] * v[i];
+        if (vv > 0.0) {
+            for (int j = k; j < m; j++) {
+                double t = 0.0;
+                for (int i = k; i < n; i++) t += v[i] * M[i + (size_t)j * n];
+                t = 2.0 * t / vv;
+                for (int i = k; i < n; i++) M[i + (size_t)j * n] -= t * v[i];
+            }
+            for (int i = 0; i < n; i++) {
+                double t = 0.0;
+                for (int l = k; l < n; l++) t += Q[i + (size_t)l * n] * v[l];
+                t = 2.0 * t / vv;
+                for (int l = k; l < n; l++) Q[i + (size_t)l * n] -= t * v[l];
+            }
+        }
+        r++;
+    }
+    /* A^T Pi = Q R  =>  R1^T (Q1^T C) = (Pi^T b)[0:r] */
+    std::vector<double> w(r);
+    for (int i = 0; i < r; i++) {
+        double a = b[perm[i]];
+        for (int l = 0; l < i; l++) a -= M[l + (size_t)i * n] * w[l];
+        w[i] = a / M[i + (size_t)i * n];
+    }
+    Cpart.assign(n, 0.0);
+    for (int l = 0; l < r; l++)
+        for (int i = 0; i < n; i++) Cpart[i] += Q[i + (size_t)l * n] * w[l];
+    double bmax = 0.0, res = 0.0;
+    for (int j = 0; j < m; j++) {
+        double a = -b[j];
+        for (int i = 0; i < n; i++) a += A[j + (size_t)i * m] * Cpart[i];
+        res = std::max(res, std::fabs(a));
+        bmax = std::max(bmax, std::fabs(b[j]));
+    }
+    if (res > 1e-8 * (1.0 + bmax)) return fail(NTGB_EINVAL, "linear equality constraints are inconsistent (residual %g)", res);
+    nr = n - r;
+    N.resize((size_t)nr * n);
+    for (int k = 0; k < nr; k++)
+        for (int i = 0; i < n; i++) N[(size_t)k * n + i] = Q[i + (size_t)(r + k) * n];
+    return 0;
+}
+
 int check_avs(const AV *av, int n, const ntgb_setup *s, const char *what)
 {
     if (n < 0 || (n > 0 && av == nullptr)) return fail(NTGB_EINVAL, "%s: bad active-variable list", what);
@@ -390,6 +631,8 @@ void ntgb_destroy(ntgb_problem *pb)
     if (pb->ls.Ct) cudaFree(pb->ls.Ct);
     if (pb->ls.res) cudaFree(pb->ls.res);
     if (pb->ls.lv) cudaFree(pb->ls.lv);
+    if (pb->red.blob) cudaFree(pb->red.blob);
+    if (pb->red.iblob) cudaFree(pb->red.iblob);
     for (auto &h : pb->hs) {
         double *hsp[] = {h.C, h.f, h.g, h.c, h.J, h.Z, h.result};
         for (double *p : hsp)
@@ -710,6 +953,8 @@ int ntgb_create(ntgb_problem **out, const ntgb_setup *s, int device)
         for (int r = 0; r < s->nlfc; r++, bsrc++) put(&pb->lfc[(size_t)r * T.nz], nbps - 1, false, pb->lowerb[bsrc], pb->upperb[bsrc]);
         if ((rc = dev_upload(pb, &pb->dAband, band.data(), band.size()))) return rc;
         if ((rc = dev_upload(pb, &pb->dAcol0, acol0.data(), acol0.size()))) return rc;
+        pb->lin_lb = llb;
+        pb->lin_ub = lub;
         if ((rc = dev_upload(pb, &pb->dlin_lb, llb.data(), llb.size()))) return rc;
         if ((rc = dev_upload(pb, &pb->dlin_ub, lub.data(), lub.size()))) return rc;
     }
@@ -977,6 +1222,103 @@ int ntgb_linesearch(ntgb_problem *pb, int P, const double *C, const double *dC, 
     }
     CUDA_TRY(launch(k_ls_pick, (unsigned)((P + 127) / 128), 128, st, pb->ls.res, lin ? pb->ls.lv : nullptr, alpha, P,
                     nalpha, mu, c1, phi0, dphi0, C, dC, d.nC, alpha_best, phi_best, C_new));
+    return 0;
+}
+
+int ntgb_solve_eq(ntgb_problem *pb, int P, double *C, double *f, int *iters, int *status,
+                  const ntgb_solve_opts *opts, void *stream)
+{
+    if (!pb || !C) return fail(NTGB_EINVAL, "ntgb_solve_eq: null argument");
+    if (P <= 0) return 0;
+    const ntgb_dims &dm = pb->dims;
+    if (dm.ncnln > 0) return fail(NTGB_EINVAL, "ntgb_solve_eq: problem has %d nonlinear constraints", dm.ncnln);
+    for (int i = 0; i < dm.nclin; i++)
+        if (pb->lin_lb[i] != pb->lin_ub[i])
+            return fail(NTGB_EINVAL, "ntgb_solve_eq: linear constraint %d is not an equality", i);
+    ntgb_solve_opts o{200, 1e-9, 1e-4, 4};
+    if (opts) {
+        if (opts->max_iter > 0) o.max_iter = opts->max_iter;
+        if (opts->gtol > 0.0) o.gtol = opts->gtol;
+        if (opts->c1 > 0.0) o.c1 = opts->c1;
+        if (opts->check_every > 0) o.check_every = opts->check_every;
+    }
+    DeviceGuard dg(pb->device);
+    if (!dg.ok) return fail(NTGB_ECUDA, "cannot select device %d", pb->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nC = dm.nC;
+    int rc;
+    if (!pb->red.ready) {
+        std::vector<double> N, Cpart;
+        int nr = 0;
+        if ((rc = reduce_linear(pb->A, dm.nclin, nC, pb->lin_lb, N, Cpart, nr))) return rc;
+        if (nr > kSolveMaxNr)
+            return fail(NTGB_ELIMIT, "ntgb_solve_eq: %d free directions after eliminating the linear constraints (limit %d)",
+                        nr, kSolveMaxNr);
+        pb->red.nr = nr;
+        if (N.empty()) N.push_back(0.0);
+        if ((rc = dev_upload(pb, &pb->red.N, N.data(), N.size()))) return rc;
+        if ((rc = dev_upload(pb, &pb->red.Cpart, Cpart.data(), Cpart.size()))) return rc;
+        pb->red.ready = true;
+    }
+    const int nr = pb->red.nr;
+    constexpr int kNalpha = 12;
+    if (P > pb->red.cap) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (pb->red.blob) cudaFree(pb->red.blob);
+        if (pb->red.iblob) cudaFree(pb->red.iblob);
+        pb->red.blob = nullptr; pb->red.iblob = nullptr; pb->red.cap = 0;
+        const size_t nd = (size_t)P * ((size_t)4 * nr + (size_t)nr * nr + 2 * (size_t)nC + 5) + kNalpha;
+        CUDA_TRY(cudaMalloc((void **)&pb->red.blob, nd * sizeof(double)));
+        CUDA_TRY(cudaMalloc((void **)&pb->red.iblob, ((size_t)3 * P + 1) * sizeof(int)));
+        pb->red.cap = P;
+    }
+    const size_t cap = (size_t)pb->red.cap;
+    double *q = pb->red.blob;
+    double *y = q;      q += cap * nr;
+    double *yp = q;     q += cap * nr;
+    double *grp = q;    q += cap * nr;
+    double *d = q;      q += cap * nr;
+    double *H = q;      q += cap * nr * nr;
+    double *dC = q;     q += cap * nC;
+    double *g = q;      q += cap * nC;
+    double *fv = q;     q += cap;
+    double *phi0 = q;   q += cap;
+    double *dphi0 = q;  q += cap;
+    double *ab = q;     q += cap;
+    double *pbest = q;  q += cap;
+    double *alphas = q;
+    int *state = pb->red.iblob, *its = state + cap, *fails = its + cap, *count = fails + cap;
+    double ha[kNalpha];
+    for (int a = 0; a < kNalpha; a++) ha[a] = std::ldexp(1.0, -a);
+    CUDA_TRY(cudaMemcpyAsync(alphas, ha, sizeof ha, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(int), st));
+    const unsigned grid = (unsigned)((P + 127) / 128);
+    CUDA_TRY(launch(k_solve_init, grid, 128, st, P, nC, nr, pb->red.N, pb->red.Cpart, C, y, H, state, its, fails));
+    ntgb_eval_args a;
+    memset(&a, 0, sizeof a);
+    a.P = P; a.C = C; a.mode_obj = 2; a.mode_con = -1; a.f = fv; a.g = g; a.jac_layout = NTGB_JAC_NONE; a.stream = st;
+    for (int it = 0; it < o.max_iter; it++) {
+        if ((rc = ntgb_eval(pb, &a))) return rc;
+        CUDA_TRY(launch(k_solve_dir, grid, 128, st, P, nC, nr, pb->red.N, fv, g, o.gtol, y, yp, grp, H, d, dC, phi0,
+                        dphi0, state, fails, count));
+        if ((it + 1) % o.check_every == 0) {
+            int done = 0;
+            CUDA_TRY(cudaMemcpyAsync(&done, count, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (done >= P) break;
+        }
+        if ((rc = ntgb_linesearch(pb, P, C, dC, kNalpha, alphas, 0.0, o.c1, phi0, dphi0, ab, pbest, nullptr, st)))
+            return rc;
+        CUDA_TRY(launch(k_solve_update, grid, 128, st, P, nC, nr, pb->red.N, pb->red.Cpart, phi0, ab, pbest, d, y, H,
+                        C, state, its, fails, count));
+    }
+    if (f) {
+        a.mode_obj = 0; a.f = f; a.g = nullptr;
+        if ((rc = ntgb_eval(pb, &a))) return rc;
+    }
+    if (iters) CUDA_TRY(cudaMemcpyAsync(iters, its, sizeof(int) * (size_t)P, cudaMemcpyDeviceToDevice, st));
+    if (status) CUDA_TRY(cudaMemcpyAsync(status, state, sizeof(int) * (size_t)P, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return 0;
 }
 

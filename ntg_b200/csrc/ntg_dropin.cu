@@ -282,12 +282,49 @@ void ntg(int nout, double *bps, int nbps, int *kninterv, double **knots, int *or
 
     npsol_t npsol = (npsol_t)dlsym(RTLD_DEFAULT, "npsol_");
     if (!npsol) {
-        fprintf(stderr,
-                "ntg: NPSOL (npsol_) is not linked into this process -- it is separately licensed and not part of\n"
-                "     ntg_b200.  The problem was set up on the GPU (n=%d, nclin=%d, ncnln=%d) but cannot be solved;\n"
-                "     use the batched evaluation API (ntg_b200.h) or link NPSOL.\n",
-                NPn, NPnclin, NPncnln);
-        if (inform) *inform = NTG_INFORM_NO_NPSOL;
+        /* No NPSOL in the process.  Problems of the shipped examples' class (no nonlinear
+         * constraints, linear equalities only) are solved by the library's own reduced-space BFGS
+         * (ntgb_solve_eq) instead; everything else cannot be solved here. */
+        bool builtin = NPncnln == 0 && getenv("NTG_B200_NO_BUILTIN_SOLVER") == nullptr;
+        for (int i = 0; builtin && i < NPnclin; i++) builtin = bl[NPn + i] == bu[NPn + i];
+        int rc = NTGB_EINVAL;
+        if (builtin) {
+            double *dC = nullptr;
+            int *dst = nullptr;
+            int st = 0;
+            double fv = 0.0;
+            cudaSetDevice(device);
+            if (cudaMalloc((void **)&dC, sizeof(double) * ((size_t)NPn + 1)) == cudaSuccess &&
+                cudaMalloc((void **)&dst, sizeof(int) * 2) == cudaSuccess &&
+                cudaMemcpy(dC, initialguess, sizeof(double) * NPn, cudaMemcpyHostToDevice) == cudaSuccess) {
+                rc = ntgb_solve_eq(pb, 1, dC, dC + NPn, dst, dst + 1, nullptr, nullptr);
+                if (rc == 0 && cudaMemcpy(&st, dst + 1, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess &&
+                    cudaMemcpy(&fv, dC + NPn, sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess &&
+                    cudaMemcpy(initialguess, dC, sizeof(double) * NPn, cudaMemcpyDeviceToHost) == cudaSuccess) {
+                    if (objective) *objective = fv;
+                    /* NPSOL's codes: 0 optimal, 1 no further improvement possible, 4 iteration limit */
+                    if (inform) *inform = st == 1 ? 0 : (st == 2 ? 1 : 4);
+                    fprintf(stderr,
+                            "ntg: NPSOL (npsol_) is not linked into this process; solved with ntg_b200's built-in\n"
+                            "     reduced-space BFGS instead (n=%d, nclin=%d equalities, no nonlinear constraints).\n"
+                            "     istate, clambda and R are not set on this path.\n",
+                            NPn, NPnclin);
+                } else if (rc == 0) {
+                    rc = NTGB_ECUDA;
+                }
+            }
+            if (dC) cudaFree(dC);
+            if (dst) cudaFree(dst);
+            if (rc != 0) fprintf(stderr, "ntg: built-in solver failed: %s\n", ntgb_last_error());
+        }
+        if (rc != 0) {
+            fprintf(stderr,
+                    "ntg: NPSOL (npsol_) is not linked into this process -- it is separately licensed and not part of\n"
+                    "     ntg_b200.  The problem was set up on the GPU (n=%d, nclin=%d, ncnln=%d) but cannot be solved;\n"
+                    "     use the batched evaluation API (ntg_b200.h) or link NPSOL.\n",
+                    NPn, NPnclin, NPncnln);
+            if (inform) *inform = NTG_INFORM_NO_NPSOL;
+        }
     } else {
         npsoloption("nolist");                 /* src/ntg.c:248 */
         npsoloption("derivative level = 3");   /* src/ntg.c:249 */

@@ -13,7 +13,7 @@ from typing import Dict, Optional
 import numpy as np
 
 from . import abi
-from .abi import (JAC_BAND, JAC_DENSE, JAC_NONE, BuiltSetup, NtgbDims, NtgbEvalArgs, NtgbPack,
+from .abi import (JAC_BAND, JAC_DENSE, JAC_NONE, BuiltSetup, NtgbDims, NtgbEvalArgs, NtgbPack, SolveOpts,
                   ProblemSpec, c_double_p, c_int_p)
 
 _LIBDIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
@@ -48,6 +48,9 @@ def core() -> C.CDLL:
         lib.ntgb_get_linear.argtypes = [C.c_void_p, c_double_p]
         lib.ntgb_get_bounds.argtypes = [C.c_void_p, c_double_p, c_double_p]
         lib.ntgb_eval_linear.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.ntgb_solve_eq.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]
+        lib.ntgb_solve_eq.restype = C.c_int
         lib.ntgb_linesearch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                         C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]
@@ -274,6 +277,20 @@ class Problem:
                                       alphas.data_ptr(), float(mu), float(c1), _ptr(phi0), _ptr(dphi0),
                                       ab.data_ptr(), pbest.data_ptr(), Cn.data_ptr(), st))
         return ab, pbest, Cn
+
+    def solve_eq(self, Cdev, max_iter=0, gtol=0.0, c1=0.0, check_every=0):
+        """batched reduced-space BFGS (ntgb_solve_eq); Cdev [P][nC] is overwritten with the solutions.
+        Returns f [P], iters [P], status [P] (1 converged, 2 no further decrease, 0 iteration limit)."""
+        import torch
+        P = Cdev.shape[0]
+        f = torch.zeros(P, dtype=torch.float64, device=Cdev.device)
+        it = torch.zeros(P, dtype=torch.int32, device=Cdev.device)
+        stt = torch.zeros(P, dtype=torch.int32, device=Cdev.device)
+        opts = SolveOpts(int(max_iter), float(gtol), float(c1), int(check_every))
+        st = torch.cuda.current_stream(Cdev.device).cuda_stream
+        _check(core().ntgb_solve_eq(self._h, P, Cdev.data_ptr(), f.data_ptr(), it.data_ptr(), stt.data_ptr(),
+                                    C.addressof(opts), st))
+        return f, it, stt
 
     def spline_interp(self, Cdev, tdev):
         import torch

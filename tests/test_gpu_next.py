@@ -144,16 +144,12 @@ def test_ntg_dropin_with_constraints_dense_jacobian(port):
     assert_bitexact(r["A"], o["A"], "A")
 
 
-def test_ntg_without_npsol_reports_it(capfd):
-    """NPSOL absent -> ntg() sets up on the GPU, says so, sets inform, solves nothing."""
-    import subprocess
-    import sys
-    code = r'''
+_NTG_NO_NPSOL_CODE = r"""
 import ctypes as C, sys
 sys.path.insert(0, %r)
 from ntg_b200 import problem, configs
 from ntg_b200.abi import BuiltSetup
-spec = configs.vanderpol(20, constraints=False)
+spec = configs.vanderpol(20, constraints=%s)
 lib = problem.load_pack("vdp")
 s = BuiltSetup(spec, lambda role, sym: C.cast(getattr(lib, sym), C.c_void_p).value).struct
 core = problem.core()
@@ -162,16 +158,57 @@ inform, obj = C.c_int(0), C.c_double(0.0)
 x0 = (C.c_double * n)(*([1.0] * n))
 core.ntg.restype = None
 core.ntg(s.nout, s.bps, s.nbps, s.kninterv, s.knots, s.order, s.mult, s.maxderiv, x0,
-         s.nlic, s.lic, s.nltc, s.ltc, s.nlfc, s.lfc, 0, None, 0, None, 0, None, 0, None, 0, None, 0, None,
+         s.nlic, s.lic, s.nltc, s.ltc, s.nlfc, s.lfc, 0, None, s.nnltc, C.c_void_p(s.nltcf), 0, None,
+         0, None, s.ntrajectoryconstrav, s.trajectoryconstrav, 0, None,
          s.lowerb, s.upperb, 0, None, 1, C.c_void_p(s.ucf), 0, None, 0, None,
          s.ntrajectorycostav, s.trajectorycostav, 0, None,
-         (C.c_int * (n + 3))(), (C.c_double * (n + 3))(), (C.c_double * ((n + 1) ** 2))(),
+         (C.c_int * (n + 8 + 3 * 20))(), (C.c_double * (n + 8 + 3 * 20))(), (C.c_double * ((n + 1) ** 2))(),
          C.byref(inform), C.byref(obj))
 print("INFORM", inform.value)
-''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
-    assert "INFORM -1000" in p.stdout, p.stdout + p.stderr
-    assert "NPSOL" in p.stderr
+print("OBJ %%.17g" %% obj.value)
+print("X", " ".join("%%.17g" %% v for v in x0))
+"""
+
+
+def _run_ntg_no_npsol(constraints, env=None):
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    e.update(env or {})
+    p = subprocess.run([sys.executable, "-c", _NTG_NO_NPSOL_CODE % (root, constraints)], capture_output=True,
+                       text=True, timeout=300, env=e)
+    return p.stdout, p.stderr
+
+
+def test_ntg_without_npsol_reports_it():
+    """NPSOL absent and a problem with nonlinear constraints (or the built-in solver switched off)
+    -> ntg() sets up on the GPU, says so, sets inform, solves nothing."""
+    out, err = _run_ntg_no_npsol(True)
+    assert "INFORM -1000" in out, out + err
+    assert "NPSOL" in err
+    out, err = _run_ntg_no_npsol(False, {"NTG_B200_NO_BUILTIN_SOLVER": "1"})
+    assert "INFORM -1000" in out, out + err
+
+
+def test_ntg_without_npsol_solves_equality_problems(port):
+    """NPSOL absent, van der Pol as shipped (linear equalities only, examples/vanderpol.c:159-169):
+    ntg() falls back to the built-in reduced-space BFGS and returns a feasible stationary point."""
+    out, err = _run_ntg_no_npsol(False)
+    lines = dict(l.split(" ", 1) for l in out.strip().splitlines() if " " in l)
+    assert int(lines["INFORM"]) in (0, 1), out + err
+    assert "built-in" in err
+    x = np.array([float(v) for v in lines["X"].split()])
+    spec = configs.vanderpol(20, constraints=False)
+    o = port.eval(spec, x[None, :], mode_obj=2, mode_con=-1, dense=False, band=False, linear=True)
+    nC = spec.nC
+    A, b = o["A"], o["bl"][nC:nC + spec.nclin]
+    assert np.abs(A @ x - b).max() < 1e-10
+    assert abs(float(lines["OBJ"]) - o["f"][0]) <= 1e-12 * abs(o["f"][0])
+    N = _null_basis(A)
+    assert np.abs(o["g"][0] @ N).max() < 1e-6
+    f1 = port.eval(spec, np.ones((1, nC)), mode_obj=0, mode_con=-1, dense=False, band=False)["f"][0]
+    assert o["f"][0] < f1
 
 
 @pytest.mark.parametrize("name", ["cfg3_kincar", "endpoint"])
@@ -210,4 +247,105 @@ def test_batched_merit_linesearch(port, name):
     assert_close(pbest.cpu().numpy(), want_phi, "merit at the chosen step")
     assert np.array_equal(ab.cpu().numpy(), want_a), "chosen step sizes"
     assert_bitexact(Cn.cpu().numpy(), X + want_a[:, None] * D, "updated coefficients")
+    pb.close()
+
+
+def _null_basis(A):
+    """orthonormal null-space basis of A by SVD (independent of the library's Householder QR)"""
+    if A.shape[0] == 0:
+        return np.eye(A.shape[1])
+    u, s, vt = np.linalg.svd(A)
+    r = int((s > 1e-11 * s[0]).sum())
+    return vt[r:].T
+
+
+def test_batched_solve_quadratic_kkt(port):
+    """ntgb_solve_eq on the kinematic-car lane change without nonlinear constraints (the shipped
+    example's problem class, examples/kincar.c:319-339): the cost is a convex quadratic in C and
+    the constraints are linear equalities, so every initial guess must reach THE solution of the
+    KKT system assembled on the host from the oracle's gradient and A."""
+    import torch
+    from ntg_b200 import Problem
+    spec = configs.kincar(20, constraints=False, name="solve_kincar")
+    nC = spec.nC
+    o = port.eval(spec, np.zeros((1, nC)), dense=False, band=False, linear=True)
+    A, b = o["A"], o["bl"][nC:nC + spec.nclin]
+    Q = port.eval(spec, np.eye(nC), mode_obj=2, mode_con=-1, dense=False, band=False)["g"]   # g(e_i) = Q e_i
+    m = A.shape[0]
+    K = np.block([[Q, A.T], [A, np.zeros((m, m))]])
+    sol = np.linalg.lstsq(K, np.concatenate([np.zeros(nC), b]), rcond=None)[0]
+    Cstar = sol[:nC]
+    fstar = 0.5 * Cstar @ Q @ Cstar
+    P = 512
+    X = configs.coefficients("cfg3", P, spec, seed=5)
+    pb = Problem(spec, 0)
+    Cd = torch.from_numpy(X).cuda()
+    f, it, st = pb.solve_eq(Cd, max_iter=100, gtol=1e-10)
+    Cs = Cd.cpu().numpy()
+    assert (st.cpu().numpy() >= 1).all(), "every problem must terminate before the iteration limit"
+    assert np.abs(Cs @ A.T - b).max() <= 1e-9 * (1 + np.abs(b).max()), "A*C = b"
+    np.testing.assert_allclose(f.cpu().numpy(), fstar, rtol=1e-9)
+    # the minimiser is unique in the null space directions the cost sees; compare the gradient-relevant part
+    N = _null_basis(A)
+    gr = (Cs @ Q) @ N
+    assert np.abs(gr).max() <= 1e-6 * max(1.0, abs(fstar))
+    assert it.cpu().numpy().max() <= 100
+    pb.close()
+
+
+def test_batched_solve_vanderpol_vs_scipy(port):
+    """ntgb_solve_eq on the van der Pol problem of examples/vanderpol.c:159-169 (3 linear equality
+    constraints, no nonlinear ones) from 256 random initial guesses: feasibility, first-order
+    optimality checked with the ORACLE's gradient, and the cost against scipy's SLSQP started from
+    the same guesses (it may stop in a different local minimum: ours must not be worse by more than
+    rounding when both stop at the same point, and a few are compared point-wise)."""
+    import torch
+    from scipy.optimize import minimize
+    from ntg_b200 import Problem
+    spec = configs.vanderpol(20, constraints=False, name="solve_vdp")
+    nC = spec.nC
+    o = port.eval(spec, np.zeros((1, nC)), dense=False, band=False, linear=True)
+    A, b = o["A"], o["bl"][nC:nC + spec.nclin]
+    P = 256
+    X = configs.coefficients("cfg2", P, spec, seed=9)
+    pb = Problem(spec, 0)
+    Cd = torch.from_numpy(X).cuda()
+    f, it, st = pb.solve_eq(Cd, max_iter=300, gtol=1e-9)
+    Cs, fs, sts = Cd.cpu().numpy(), f.cpu().numpy(), st.cpu().numpy()
+    assert (sts >= 1).mean() > 0.98
+    assert np.abs(Cs @ A.T - b).max() <= 1e-9
+    r = port.eval(spec, Cs, mode_obj=2, mode_con=-1, dense=False, band=False)
+    assert_close(fs, r["f"], "final cost equals the oracle's at the returned point")
+    N = _null_basis(A)
+    gr = np.abs(r["g"] @ N).max(axis=1)
+    ok = sts == 1
+    assert (gr[ok] <= 1e-6 * np.maximum(1.0, np.abs(fs[ok]))).all(), gr[ok].max()
+    # feasible start of each problem = projection of X onto A*C = b; the cost must not rise from it
+    y0 = (X - Cs) @ N
+    f0 = port.eval(spec, Cs + y0 @ N.T, mode_obj=0, mode_con=-1, dense=False, band=False)["f"]
+    assert (fs <= f0 + 1e-12 * np.abs(f0)).all(), "descent from the projected initial guess"
+
+    def fun(c):
+        e = port.eval(spec, c[None, :], mode_obj=2, mode_con=-1, dense=False, band=False)
+        return float(e["f"][0]), e["g"][0]
+    same = 0
+    for p in range(8):
+        res = minimize(fun, X[p], jac=True, method="SLSQP",
+                       constraints=[{"type": "eq", "fun": lambda c: A @ c - b, "jac": lambda c: A}],
+                       options={"ftol": 1e-14, "maxiter": 500})
+        if np.abs(res.x - Cs[p]).max() < 1e-3:
+            same += 1
+            assert abs(res.fun - fs[p]) <= 1e-7 * max(1.0, abs(fs[p]))
+    assert same >= 4, "most starts should reach the same local minimum as SLSQP"
+    pb.close()
+
+
+def test_solve_refuses_inequalities_and_nonlinear():
+    import torch
+    from ntg_b200 import Problem
+    from ntg_b200.problem import NtgError
+    spec = configs.kincar(20, constraints=True, name="solve_refuse")
+    pb = Problem(spec, 0)
+    with pytest.raises(NtgError):
+        pb.solve_eq(torch.zeros((4, spec.nC), dtype=torch.float64, device="cuda"))
     pb.close()

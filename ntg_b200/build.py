@@ -105,7 +105,129 @@ def pack_so(name: str) -> str:
     return os.path.join(LIB, f"libntgpack_{name}.so")
 
 
-def generate_wrapper(m: PackManifest) -> str:
+CON_ROLES = ("nlicf", "nltcf", "nlfcf")
+
+
+def probe_sparsity(m: PackManifest, verbose: bool = False) -> Dict[str, List[int]]:
+    """Which entries of its derivative vector does each callback ever set to something other
+    than +0.0?  The user's file is compiled once more with gcc (plain C, main() renamed,
+    unresolved library symbols left alone -- nothing but the callbacks is called) together with
+    a small generated main() that calls every callback at 48 points in modes 1 and 2 and prints,
+    per derivative row, a bit mask over iz_j + l.  The kernels use the masks to skip the chain-rule
+    terms of entries that are structurally zero and CHECK the assumption on the device at every
+    evaluation (ntg_eval_small.cuh::sp_clean), so a wrong probe costs speed, never correctness.
+    Returns {} when the probe cannot be built or run (the kernels then treat everything as dense)."""
+    base = m.name[:-5] if m.name.endswith("_fast") else m.name
+    os.makedirs(GEN, exist_ok=True)
+    cache = os.path.join(GEN, f"probe_{base}.txt")
+    src = os.path.abspath(m.src)
+    roles = {r: fn for r, fn in m.callbacks.items() if fn}
+    key = "key " + repr((sorted(roles.items()), m.maxderiv, sorted(m.counts.items())))
+
+    def parse(text: str) -> Dict[str, List[int]]:
+        out: Dict[str, List[int]] = {}
+        for line in text.splitlines():
+            w = line.split()
+            if len(w) >= 2 and w[0] in SIGS:
+                out[w[0]] = [int(x, 16) for x in w[1:]]
+        return out
+
+    if os.path.exists(cache) and not _newer(cache, [src, os.path.abspath(__file__)]):
+        text = open(cache).read()
+        if text.startswith(key + "\n"):
+            return parse(text)
+    nout = len(m.maxderiv)
+    L = []
+    for h in ("assert.h", "float.h", "math.h", "stdio.h", "stdlib.h", "string.h", "unistd.h"):
+        L.append(f"#include <{h}>")
+    L.append('#include "ntg.h"')
+    L.append("#define main ntg_probe_user_main_")
+    L.append(f'#include "{src}"')
+    L.append("#undef main")
+    L.append("static unsigned long long s_ = 88172645463325252ULL;")
+    L.append("static double rnd_(void) { s_ ^= s_ << 13; s_ ^= s_ >> 7; s_ ^= s_ << 17; "
+             "return (double)(s_ >> 11) / 9007199254740992.0 * 6.0 - 3.0; }")
+    L.append("int main(void) {")
+    L.append(f"    enum {{ NOUT_ = {nout}, MAXC_ = 64 }};")
+    L.append("    int md_[NOUT_] = {" + ", ".join(f"({e})" for e in m.maxderiv) + "};")
+    L.append("    int nz_ = 0, j_, l_, t_, mode_, r_;")
+    L.append("    double z_[512], *zp_[NOUT_], f_[MAXC_], dfs_[MAXC_][512], *dfp_[MAXC_];")
+    L.append("    unsigned long long mask_[6][MAXC_];")
+    L.append("    memset(mask_, 0, sizeof mask_);")
+    L.append("    for (j_ = 0; j_ < NOUT_; j_++) { zp_[j_] = z_ + nz_; nz_ += md_[j_]; }")
+    L.append("    if (nz_ > 64) return 2;")
+    L.append("    for (r_ = 0; r_ < MAXC_; r_++) dfp_[r_] = dfs_[r_];")
+    L.append("    for (t_ = 0; t_ < 48; t_++) {")
+    L.append("        for (l_ = 0; l_ < nz_; l_++) z_[l_] = t_ == 0 ? 0.0 : (t_ == 1 ? 1.0 : (t_ == 2 ? -1.0 : rnd_()));")
+    L.append("        for (mode_ = 1; mode_ <= 2; mode_++) {")
+    L.append("            int nstate_ = t_ == 3 ? 1 : 0, i_ = t_ % 7, mo_;")
+    order = list(SIGS)
+    for ri, role in enumerate(order):
+        fn = roles.get(role)
+        if not fn:
+            continue
+        if role in CON_ROLES:
+            cnt = m.counts.get(role, "0")
+            L.append(f"            if (({cnt}) > MAXC_) return 3;")
+            L.append("            memset(dfs_, 0, sizeof dfs_); memset(f_, 0, sizeof f_); mo_ = mode_;")
+            args = "&mo_, &nstate_, " + ("&i_, " if role == "nltcf" else "") + "f_, dfp_, zp_"
+            L.append(f"            {fn}({args});")
+            L.append(f"            for (r_ = 0; r_ < ({cnt}); r_++) for (l_ = 0; l_ < nz_; l_++) {{")
+            L.append("                unsigned long long b_; memcpy(&b_, &dfs_[r_][l_], 8);")
+            L.append(f"                if (b_ != 0) mask_[{ri}][r_] |= 1ULL << l_; }}")
+        else:
+            L.append("            memset(dfs_, 0, sizeof dfs_); memset(f_, 0, sizeof f_); mo_ = mode_;")
+            args = "&mo_, &nstate_, " + ("&i_, " if role == "ucf" else "") + "f_, dfs_[0], zp_"
+            L.append(f"            {fn}({args});")
+            L.append("            for (l_ = 0; l_ < nz_; l_++) {")
+            L.append("                unsigned long long b_; memcpy(&b_, &dfs_[0][l_], 8);")
+            L.append(f"                if (b_ != 0) mask_[{ri}][0] |= 1ULL << l_; }}")
+    L.append("        }")
+    L.append("    }")
+    for ri, role in enumerate(order):
+        if not roles.get(role):
+            continue
+        cnt = m.counts.get(role, "0") if role in CON_ROLES else "1"
+        L.append(f'    printf("{role}"); for (r_ = 0; r_ < ({cnt}); r_++) printf(" %llx", mask_[{ri}][r_]); printf("\\n");')
+    L.append("    return 0;")
+    L.append("}")
+    csrc = os.path.join(GEN, f"probe_{base}.c")
+    exe = os.path.join(GEN, f"probe_{base}")
+    with open(csrc, "w") as fh:
+        fh.write("\n".join(L) + "\n")
+    # the NTG entry points a user program calls from main() (include/ntg.h): never called by the
+    # probe, defined here only so that it links without the CUDA library
+    stubs = os.path.join(GEN, "probe_stubs.c")
+    with open(stubs, "w") as fh:
+        fh.write("#include <stdlib.h>\n" + "".join(
+            f"void {n}() {{ abort(); }}\n" for n in
+            ("ntg", "npsoloption", "linspace", "printNTGBanner", "MakeMatrix", "FreeMatrix", "DoubleMatrix",
+             "FreeDoubleMatrix", "PrintMatrix", "PrintVector", "PrintiVector", "SplineInterp")))
+    gcc = shutil.which("gcc")
+    text = ""
+    try:
+        if gcc is None:
+            raise RuntimeError("gcc not found")
+        cmd = [gcc, "-O0", "-w", "-I", INCLUDE, "-o", exe, csrc, stubs, "-lm"]
+        if verbose:
+            print("+", " ".join(cmd), flush=True)
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+        if r.returncode != 0:
+            raise RuntimeError(r.stderr[-400:])
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+        if r.returncode != 0:
+            raise RuntimeError(f"probe exited {r.returncode}")
+        text = r.stdout
+    except Exception as e:  # dense masks are always correct
+        if verbose:
+            print(f"sparsity probe of pack {m.name} unavailable ({e}); treating derivatives as dense", flush=True)
+        text = ""
+    with open(cache, "w") as fh:
+        fh.write(key + "\n" + text)
+    return parse(text)
+
+
+def generate_wrapper(m: PackManifest, verbose: bool = False) -> str:
     os.makedirs(GEN, exist_ok=True)
     out = os.path.join(GEN, f"pack_{m.name}.cu")
     nout = len(m.maxderiv)
@@ -158,6 +280,17 @@ def generate_wrapper(m: PackManifest) -> str:
         fn = f"::{fn}" if fn else "nullptr"
         L.append(f"    static constexpr {ROLE_T[role]} cb_{role} = {fn};")
         L.append(f"    static {ROLE_T[role]} cb_{role}_host() {{ return {fn}; }}")
+    # structural sparsity of the derivative vectors (probe_sparsity): bit iz_j + l
+    sp = probe_sparsity(m, verbose)
+    for role in SIGS:
+        masks = sp.get(role) if m.callbacks.get(role) else None
+        if role in CON_ROLES:
+            body = ("constexpr unsigned long long t[] = {" + ", ".join(f"0x{v:x}ull" for v in masks) + "}; return t[m];"
+                    if masks else "return ~0ull;")
+            L.append(f"    __host__ __device__ static constexpr unsigned long long sp_{role}(int m) {{ {body} }}")
+        else:
+            v = f"0x{masks[0]:x}ull" if masks else "~0ull"
+            L.append(f"    __host__ __device__ static constexpr unsigned long long sp_{role}() {{ return {v}; }}")
     L.append("};")
     L.append(f"NTGB_DEFINE_PACK({m.name}, {tn}, {1 if m.exact else 0})")
     text = "\n".join(L) + "\n"
@@ -169,13 +302,14 @@ def generate_wrapper(m: PackManifest) -> str:
 
 def build_pack(m: PackManifest, verbose: bool = False, force: bool = False, ptxas_v: bool = False) -> str:
     core = build_core(verbose)
-    wrapper = generate_wrapper(m)
+    wrapper = generate_wrapper(m, verbose)
     so = pack_so(m.name)
     deps = [wrapper, os.path.abspath(m.src), core, os.path.join(CSRC, "ntg_eval_kernel.cuh"), os.path.join(CSRC, "ntg_eval_small.cuh"), os.path.join(CSRC, "ntg_eval_cluster.cuh"),
             os.path.join(CSRC, "ntg_kernel_args.h"), os.path.join(INCLUDE, "ntg_b200.h"),
             os.path.join(INCLUDE, "ntg.h")]
     if force or ptxas_v or _newer(so, deps):
         cmd = [nvcc()] + ARCH + COMMON + ["-fmad=false" if m.exact else "-fmad=true"]
+        cmd += os.environ.get("NTG_B200_NVCC_EXTRA", "").split()
         if ptxas_v:
             cmd += ["-Xptxas", "-v"]
         cmd += ["-o", so, wrapper, "-L", LIB, "-lntg_b200", "-Xlinker", "-rpath=$ORIGIN", "-Xlinker", "-Bsymbolic"]

@@ -835,6 +835,50 @@ int ntgb_create(ntgb_problem **out, const ntgb_setup *s, int device)
         int *dseg0 = nullptr;
         if ((rc = dev_upload(pb, &dseg0, seg0.data(), (size_t)T.nC))) return rc;
         T.col_seg0 = dseg0;
+
+        /* K1s quadrature schedule (ntg_kernel_args.h): longest-chain-first packing of the nC+1
+         * chains into the slots a 256-thread CTA has for GR = G*(r+1) problems per tile */
+        T.sched_G = 0;
+        T.sched = nullptr;
+        if (nbps <= NTGB_SCHED_BLOCK) {
+            const int G0 = NTGB_SCHED_BLOCK / nbps, ncol = T.nC + 1, stride = NTGB_SCHED_BLOCK + 1 + ncol;
+            std::vector<int> len((size_t)ncol), order((size_t)ncol);
+            for (int c = 0; c < T.nC; c++) {
+                const int i0 = lo[c] > 0 ? lo[c] - 1 : 0;
+                const int nend = (hi[c] < nbps - 2 ? hi[c] : nbps - 2) + 1;
+                len[c] = nend > i0 ? nend - i0 : 0;
+            }
+            len[T.nC] = nbps - 1;
+            for (int c = 0; c < ncol; c++) order[c] = c;
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return len[a] > len[b]; });
+            std::vector<int> sched((size_t)8 * stride, 0);
+            for (int r = 0; r < 8; r++) {
+                const int GR = G0 * (r + 1);
+                const int lanes = GR < NTGB_SCHED_BLOCK ? GR : NTGB_SCHED_BLOCK;
+                int NS = NTGB_SCHED_BLOCK / lanes;
+                if (NS > ncol) NS = ncol;
+                T.sched_ns[r] = NS;
+                std::vector<long long> load((size_t)NS, 0);
+                std::vector<std::vector<int>> lists((size_t)NS);
+                for (int c : order) {
+                    int best = 0;
+                    for (int q = 1; q < NS; q++)
+                        if (load[q] < load[best]) best = q;
+                    load[best] += len[c] + 4; /* + a fixed cost per chain */
+                    lists[best].push_back(c);
+                }
+                int *st = &sched[(size_t)r * stride], *cols = st + NTGB_SCHED_BLOCK + 1, pos = 0;
+                for (int q = 0; q < NS; q++) {
+                    st[q] = pos;
+                    for (int c : lists[q]) cols[pos++] = c;
+                }
+                for (int q = NS; q <= NTGB_SCHED_BLOCK; q++) st[q] = pos;
+            }
+            int *dsched = nullptr;
+            if ((rc = dev_upload(pb, &dsched, sched.data(), sched.size()))) return rc;
+            T.sched = dsched;
+            T.sched_G = G0;
+        }
     }
 
     /* do all outputs share one spline setup (one table serves all)? */

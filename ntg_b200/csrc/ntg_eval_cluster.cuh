@@ -248,7 +248,7 @@ ntg_eval_cluster_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL, int
                     fall0[buf * nbps + bp] = fv; /* distributed shared memory: rank 0 collects the integrand */
                     if (obj_d) {
                         double *Dp = D_s + lbp;
-                        band_from_regs<PK, FULL, true>(T, Bt, df, [&](auto, int, double v) {
+                        band_from_regs<PK, FULL, true>(T, Bt, df, [&](auto, auto, double v) {
                             *Dp = v;
                             Dp += bpc;
                         });
@@ -268,7 +268,7 @@ ntg_eval_cluster_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL, int
                     sc0[buf * 2 + 0] = fv;
                     if (obj_d) {
                         double *Dp = DI_s;
-                        band_from_regs<PK, FULL, true>(T, Bt, df, [&](auto, int, double v) { *Dp++ = v; });
+                        band_from_regs<PK, FULL, true>(T, Bt, df, [&](auto, auto, double v) { *Dp++ = v; });
                     }
                 }
             }
@@ -285,7 +285,7 @@ ntg_eval_cluster_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL, int
                     sc0[buf * 2 + 1] = fv;
                     if (obj_d) {
                         double *Dp = DF_s;
-                        band_from_regs<PK, FULL, true>(T, Bt, df, [&](auto, int, double v) { *Dp++ = v; });
+                        band_from_regs<PK, FULL, true>(T, Bt, df, [&](auto, auto, double v) { *Dp++ = v; });
                     }
                 }
             }
@@ -330,15 +330,16 @@ ntg_eval_cluster_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL, int
                             if (A.jac_layout == NTGB_JAC_BAND) {
                                 double *ptr = A.J + (size_t)p * T.ncnln * S + (size_t)T.nnlic * S +
                                               (size_t)m * S * nbps + bp;
-                                band_from_regs<PK, FULL, true>(T, Bt, dfc[m], [&](auto, int, double v) {
+                                band_from_regs<PK, FULL, true>(T, Bt, dfc[m], [&](auto, auto, double v) {
                                     st_stream(ptr, v);
                                     ptr += nbps;
                                 });
                             } else {
                                 double *Jp = A.J + (size_t)p * T.ncnln * nC;
                                 const int row = T.nnlic + m * nbps + bp;
-                                band_from_regs<PK, FULL, true>(T, Bt, dfc[m], [&](auto jc, int k, double v) {
+                                band_from_regs<PK, FULL, true>(T, Bt, dfc[m], [&](auto jc, auto kc, double v) {
                                     constexpr int j = decltype(jc)::value;
+                                    constexpr int k = decltype(kc)::value;
                                     st_stream(Jp + (size_t)(T.iC[j] + offj[j] + k) * T.ncnln + row, v);
                                 });
                             }

@@ -35,6 +35,10 @@
 
 #include "ntg_eval_kernel.cuh"
 
+#ifndef NTG_DBG
+#define NTG_DBG 0 /* scratch experiments: 1 skip phase B, 2 no Jacobian stores, 4 no phase-A shared stores */
+#endif
+
 namespace ntgb {
 
 template <class PK>
@@ -59,11 +63,11 @@ struct SmallSmem {
     __host__ __device__ size_t DF_off() const { return DI_off() + (size_t)GR * S; }           /* [GR][S]        */
     __host__ __device__ size_t cI_off() const { return DF_off() + (size_t)GR * S; }           /* [GR]           */
     __host__ __device__ size_t cF_off() const { return cI_off() + GR; }                       /* [GR]           */
-    __host__ __device__ size_t viol_off() const { return cF_off() + GR; }                     /* [GR] u64       */
-    __host__ __device__ size_t dt_off() const { return viol_off() + GR; }                     /* [nbps]         */
+    __host__ __device__ size_t viol_off() const { return cF_off() + GR; }                     /* [nbps][GRP]    */
+    __host__ __device__ size_t dt_off() const { return viol_off() + (size_t)nbps * GRP(); }   /* [nbps]         */
     __host__ __device__ size_t C_off() const { return dt_off() + nbps; }                      /* [2][GR*nC]     */
     __host__ __device__ size_t seg_off() const { return C_off() + 2 * (size_t)GR * nC; }      /* int [2][segtot] */
-    __host__ __device__ size_t bytes() const { return seg_off() * 8 + 2 * (size_t)segtot * 4 + 8; }
+    __host__ __device__ size_t bytes() const { return seg_off() * 8 + (2 * (size_t)segtot + 4 + (size_t)(nC + 1) * 10) * 4 + 8; }
 };
 
 __device__ __forceinline__ void cp_async8(double *dst_smem, const double *src)
@@ -74,9 +78,29 @@ __device__ __forceinline__ void cp_async8(double *dst_smem, const double *src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
+/* Structural sparsity of a callback's derivative vector (bit iz_j + l set = the callback may write
+ * a non-zero there), probed when the pack is built (ntg_b200/build.py::probe_sparsity).  Terms of
+ * a structurally zero entry are skipped: the reference adds (+0.0 * B) to an accumulator that
+ * starts at +0.0 and can therefore never be -0.0, so for finite B the skipped additions do not
+ * change a single bit.  The kernels still CHECK that the entries are +0.0 (sp_clean) and take
+ * the dense path otherwise; when the callback really never writes them the compiler has already
+ * propagated the zeros and the check folds away. */
+constexpr unsigned long long kDense = ~0ull;
+
+template <int NZ>
+__device__ __forceinline__ bool sp_clean(const double *df, unsigned long long mask)
+{
+    bool ok = true;
+#pragma unroll
+    for (int l = 0; l < NZ; l++)
+        if (!((mask >> l) & 1ull)) ok = ok && (__double_as_longlong(df[l]) == 0ll);
+    return ok;
+}
+
 /* band row from the register-resident table:
- * sink(slot) gets sum_l dz[iz_j + l] * B_j[bp][k][l], l ascending from 0.0, slots in (j,k) order */
-template <class PK, bool FULL, bool ONE = false, class F>
+ * sink(j, k, value) gets sum_l dz[iz_j + l] * B_j[bp][k][l], l ascending from 0.0, slots in (j,k)
+ * order; j and k arrive as integral constants */
+template <class PK, bool FULL, bool ONE = false, unsigned long long MASK = kDense, class F>
 __device__ __forceinline__ void band_from_regs(const ntgb_devtab &T, const double *Bt, const double *dz, F &&sink)
 {
     static_for<0, PK::kNout>([&](auto jc) {
@@ -85,16 +109,24 @@ __device__ __forceinline__ void band_from_regs(const ntgb_devtab &T, const doubl
         constexpr int IZ = pk_iz<PK>(j);
         constexpr int TB = ONE ? 0 : pk_tab_base<PK>(j); /* ONE: every output shares table 0 */
         const int order = FULL ? PK::kMaxOrd : T.order[j];
-#pragma unroll
-        for (int k = 0; k < PK::kMaxOrd; k++) {
+        static_for<0, PK::kMaxOrd>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
             if (FULL || k < order) {
                 double acc = 0.0;
-#pragma unroll
-                for (int l = 0; l < MD; l++) acc = acc + dz[IZ + l] * Bt[TB + k * MD + l];
-                sink(jc, k, acc);
+                static_for<0, MD>([&](auto lc) {
+                    constexpr int l = decltype(lc)::value;
+                    if constexpr (((MASK >> (IZ + l)) & 1ull) != 0ull) acc = acc + dz[IZ + l] * Bt[TB + k * MD + l];
+                });
+                sink(jc, kc, acc);
             }
-        }
+        });
     });
+}
+
+template <class PK, int KIND>
+__host__ __device__ constexpr unsigned long long sp_con(int m)
+{
+    return KIND == 0 ? PK::sp_nlicf(m) : (KIND == 1 ? PK::sp_nltcf(m) : PK::sp_nlfcf(m));
 }
 
 __device__ __forceinline__ double nl_bound(const ntgb_devtab &T, bool upper, int idx)
@@ -104,46 +136,84 @@ __device__ __forceinline__ double nl_bound(const ntgb_devtab &T, bool upper, int
 }
 
 /* constraint rows of one kind evaluated at this thread's breakpoint:
- * KIND 0 initial (columns from iC_j, src/colloc.c:254), 1 trajectory, 2 final */
-template <class PK, bool FULL, int NCON, int KIND, bool ONE = false>
+ * KIND 0 initial (columns from iC_j, src/colloc.c:254), 1 trajectory, 2 final.
+ * BAND selects the layout at compile time; SPARSE uses the pack's probed sparsity masks. */
+template <class PK, bool FULL, int NCON, int KIND, bool ONE, bool BAND, bool SPARSE>
+__device__ __forceinline__ void emit_rows_layout(const ntgb_devtab &T, const ntgb_eval_args &A, const double *Bt,
+                                                 const int *offj, int p, int bp,
+                                                 const double (&dfc)[NCON][pk_nz<PK>()], int row_base)
+{
+    const int nbps = T.nbps, S = T.S;
+    if constexpr (BAND) {
+        /* J band [p][row][slot][.]: rows of a trajectory constraint are breakpoint-fastest, so a
+         * thread's stores are S*NCON strided ones.  With every order at the pack's bound the slot
+         * of (j, k) is a compile-time constant and each address is one multiply-add from one base. */
+        char *Jp = reinterpret_cast<char *>(A.J + ((size_t)p * T.ncnln + row_base) * S + (KIND == 1 ? bp : 0));
+        const unsigned stride8 = (KIND == 1 ? (unsigned)nbps : 1u) * 8u;
+        static_for<0, NCON>([&](auto mc) {
+            constexpr int m = decltype(mc)::value;
+            constexpr unsigned long long MASK = SPARSE ? sp_con<PK, KIND>(m) : kDense;
+            if constexpr (FULL) {
+                constexpr int SF = PK::kNout * PK::kMaxOrd;
+                band_from_regs<PK, FULL, ONE, MASK>(T, Bt, dfc[m], [&](auto jc, auto kc, double v) {
+                    constexpr int slot = m * SF + decltype(jc)::value * PK::kMaxOrd + decltype(kc)::value;
+                    if ((NTG_DBG & 2) && v != 1.2345e300) return;
+                    st_stream(reinterpret_cast<double *>(Jp + (size_t)stride8 * (unsigned)slot), v);
+                });
+            } else {
+                char *ptr = Jp + (size_t)stride8 * (unsigned)(m * S);
+                band_from_regs<PK, FULL, ONE, MASK>(T, Bt, dfc[m], [&](auto, auto, double v) {
+                    st_stream(reinterpret_cast<double *>(ptr), v);
+                    ptr += stride8;
+                });
+            }
+        });
+    } else {
+        double *Jp = A.J + (size_t)p * T.ncnln * T.nC;
+        static_for<0, NCON>([&](auto mc) {
+            constexpr int m = decltype(mc)::value;
+            constexpr unsigned long long MASK = SPARSE ? sp_con<PK, KIND>(m) : kDense;
+            const int row = (KIND == 1) ? row_base + m * nbps + bp : row_base + m;
+            band_from_regs<PK, FULL, ONE, MASK>(T, Bt, dfc[m], [&](auto jc, auto kc, double v) {
+                constexpr int j = decltype(jc)::value;
+                const int col = T.iC[j] + (KIND == 0 ? 0 : offj[j]) + decltype(kc)::value;
+                st_stream(Jp + (size_t)col * T.ncnln + row, v);
+            });
+        });
+    }
+}
+
+template <class PK, bool FULL, int NCON, int KIND, bool ONE = false, bool HOT = false>
 __device__ __forceinline__ void emit_rows_regs(const ntgb_devtab &T, const ntgb_eval_args &A, const double *Bt,
                                                const int *offj, int p, int bp, const double (&dfc)[NCON][pk_nz<PK>()],
                                                int row_base)
 {
-    const int nbps = T.nbps, S = T.S;
-    if (A.jac_layout == NTGB_JAC_BAND) {
-        double *Jp = A.J + (size_t)p * T.ncnln * S + (size_t)row_base * S;
-#pragma unroll
-        for (int m = 0; m < NCON; m++) {
-            if (KIND == 1) {
-                double *ptr = Jp + (size_t)m * S * nbps + bp;
-                band_from_regs<PK, FULL, ONE>(T, Bt, dfc[m], [&](auto, int, double v) {
-                    st_stream(ptr, v);
-                    ptr += nbps;
-                });
-            } else {
-                double *ptr = Jp + (size_t)m * S;
-                band_from_regs<PK, FULL, ONE>(T, Bt, dfc[m], [&](auto, int, double v) {
-                    st_stream(ptr, v);
-                    ptr += 1;
-                });
-            }
-        }
+    bool clean = true;
+    static_for<0, NCON>([&](auto mc) {
+        constexpr int m = decltype(mc)::value;
+        clean = clean && sp_clean<pk_nz<PK>()>(dfc[m], sp_con<PK, KIND>(m));
+    });
+    const bool band = HOT || A.jac_layout == NTGB_JAC_BAND;
+    if (band) {
+        if (clean) emit_rows_layout<PK, FULL, NCON, KIND, ONE, true, true>(T, A, Bt, offj, p, bp, dfc, row_base);
+        else emit_rows_layout<PK, FULL, NCON, KIND, ONE, true, false>(T, A, Bt, offj, p, bp, dfc, row_base);
     } else {
-        double *Jp = A.J + (size_t)p * T.ncnln * T.nC;
-#pragma unroll
-        for (int m = 0; m < NCON; m++) {
-            const int row = (KIND == 1) ? row_base + m * nbps + bp : row_base + m;
-            band_from_regs<PK, FULL, ONE>(T, Bt, dfc[m], [&](auto jc, int k, double v) {
-                constexpr int j = decltype(jc)::value;
-                const int col = T.iC[j] + (KIND == 0 ? 0 : offj[j]) + k;
-                st_stream(Jp + (size_t)col * T.ncnln + row, v);
-            });
-        }
+        if (clean) emit_rows_layout<PK, FULL, NCON, KIND, ONE, false, true>(T, A, Bt, offj, p, bp, dfc, row_base);
+        else emit_rows_layout<PK, FULL, NCON, KIND, ONE, false, false>(T, A, Bt, offj, p, bp, dfc, row_base);
     }
 }
 
-template <class PK, bool FULL>
+/* chain rule of a COST derivative vector through the table, with the pack's sparsity mask */
+template <class PK, bool FULL, unsigned long long MASK, class F>
+__device__ __forceinline__ void cost_band(const ntgb_devtab &T, const double *Bt, const double *df, F &&sink)
+{
+    if (sp_clean<pk_nz<PK>()>(df, MASK)) band_from_regs<PK, FULL, false, MASK>(T, Bt, df, sink);
+    else band_from_regs<PK, FULL, false, kDense>(T, Bt, df, sink);
+}
+
+/* HOT = the solver's steady state, known at compile time: funobj mode 2 + funcon mode 2, Jacobian
+ * in band layout, f / g / c / J all requested, Z not requested. */
+template <class PK, bool FULL, bool HOT = false>
 __global__ void __launch_bounds__(256, 2)
 ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R, int segtot)
 {
@@ -160,13 +230,16 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
     double *DF_s = smem + L.DF_off();
     double *cI_s = smem + L.cI_off();
     double *cF_s = smem + L.cF_off();
-    unsigned long long *viol_s = reinterpret_cast<unsigned long long *>(smem + L.viol_off());
+    double *viol_s = smem + L.viol_off();
     double *dt_s = smem + L.dt_off();
     double *C_s = smem + L.C_off();
     int *segstart_s = reinterpret_cast<int *>(smem + L.seg_off());
     int *segoff_s = segstart_s + segtot;
+    int *costseg_s = segoff_s + segtot; /* the cost as a chain: one run {0, nbps}, offset 0 */
+    int *par_s = costseg_s + 4;         /* [nC+1][9] chain description per column, see below */
+    int *cols_s = par_s + (nC + 1) * 9; /* [nC+1] the schedule's column list */
 
-    const int mode_obj = A.mode_obj, mode_con = A.mode_con;
+    const int mode_obj = HOT ? 2 : A.mode_obj, mode_con = HOT ? 2 : A.mode_con;
     const bool obj_on = mode_obj >= 0 && mode_obj <= 2;
     const bool con_on = mode_con >= 0 && mode_con <= 2 && T.ncnln > 0;
     const bool obj_d = obj_on && mode_obj != 0, obj_v = obj_on && mode_obj != 1;
@@ -178,7 +251,9 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
     const bool doCI = PK::cb_nlicf != nullptr && con_on && T.nnlic != 0;
     const bool doCT = PK::cb_nltcf != nullptr && con_on && T.nnltc != 0;
     const bool doCF = PK::cb_nlfcf != nullptr && con_on && T.nnlfc != 0;
-    const bool wantJ = con_d && A.J != nullptr && A.jac_layout != NTGB_JAC_NONE;
+    const bool wantJ = HOT || (con_d && A.J != nullptr && A.jac_layout != NTGB_JAC_NONE);
+    const bool wantZ = !HOT && A.Z != nullptr;
+    const bool want_c = HOT || A.c != nullptr;
 
     /* ---- once per CTA: dt, offset runs, accumulators; once per thread: its table slice ---- */
     for (int i = threadIdx.x; i < nbps - 1; i += blockDim.x) dt_s[i] = __ldg(T.bps + i + 1) - __ldg(T.bps + i);
@@ -193,7 +268,6 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
         }
     }
     for (int q = threadIdx.x; q < GR; q += blockDim.x) {
-        viol_s[q] = 0ull;
         cI_s[q] = 0.0;
         cF_s[q] = 0.0;
     }
@@ -217,6 +291,72 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                 Bt[TB + k * MD + d] = (active && k < order) ? __ldg(T.Bt[j] + (size_t)(k * MD + d) * nbps + bp) : 0.0;
     });
 
+    /* phase-B mapping (tile-invariant): slot and problem lane of this thread, its column list */
+    const bool want_g = HOT || (obj_d && A.g != nullptr);
+    const int lanesB = GR < (int)blockDim.x ? GR : (int)blockDim.x;
+    const int slotB = threadIdx.x / lanesB, laneB = threadIdx.x - slotB * lanesB;
+    const bool use_sched = T.sched != nullptr && blockDim.x == NTGB_SCHED_BLOCK && G == T.sched_G && R >= 1 && R <= 8;
+    const int *sched_st = use_sched ? T.sched + (size_t)(R - 1) * (NTGB_SCHED_BLOCK + 1 + nC + 1) : nullptr;
+    const int *sched_cols = use_sched ? sched_st + NTGB_SCHED_BLOCK + 1 : nullptr;
+    const int NSB = (int)blockDim.x / lanesB;
+    int it0, it1, istep;
+    if (use_sched) {
+        const bool has = slotB < T.sched_ns[R - 1];
+        it0 = has ? __ldg(sched_st + slotB) : 0;
+        it1 = has ? __ldg(sched_st + slotB + 1) : 0;
+        istep = 1;
+    } else { /* any other launch geometry: columns dealt round-robin over the slots */
+        it0 = slotB < NSB ? slotB : nC + 1;
+        it1 = nC + 1;
+        istep = NSB;
+    }
+    if (threadIdx.x == 0) {
+        costseg_s[0] = 0;
+        costseg_s[1] = nbps;
+        costseg_s[2] = 0;
+    }
+    /* chain description per column, built once (everything in it is tile-invariant):
+     * [0] first breakpoint i0, [1] last term nend (no chain when i0 >= nend), [2] run holding i0,
+     * [3]/[8] where the output's run starts / run offsets sit in segstart_s, [4] the column's base
+     * inside D_s (doubles), [5] band width, [6] local column, [7] (slot in DI)+1 | ((slot in DF)+1)<<16 */
+    for (int c = threadIdx.x; c <= nC; c += blockDim.x) {
+        int *pp = par_s + c * 9;
+        if (c == nC) {
+            pp[0] = 0; pp[1] = (doU && obj_v) ? nbps - 1 : 0; pp[2] = 0; pp[3] = 2 * segtot; pp[8] = 2 * segtot + 2;
+            pp[4] = S * nbps * GRP; /* f_s follows D_s */
+            pp[5] = 1; pp[6] = 0; pp[7] = 0;
+        } else {
+            int sb = 0;
+            pp[0] = 0; pp[1] = 0; pp[2] = 0; pp[3] = 0; pp[4] = 0; pp[5] = 0; pp[6] = 0; pp[7] = 0; pp[8] = 0;
+            for (int j = 0; j < T.nout; j++) {
+                const int clj = c - T.iC[j];
+                if (clj >= 0 && clj < T.ncoef[j]) {
+                    const int ord = T.order[j];
+                    if (doU) {
+                        const int lo = __ldg(T.col_lo + c), hi = __ldg(T.col_hi + c);
+                        pp[0] = lo > 0 ? lo - 1 : 0;
+                        pp[1] = (hi < nbps - 2 ? hi : nbps - 2) + 1;
+                        pp[2] = __ldg(T.col_seg0 + c);
+                    }
+                    pp[3] = sb;
+                    pp[8] = segtot + sb;
+                    pp[4] = T.jk0[j] * nbps * GRP;
+                    pp[5] = ord;
+                    pp[6] = clj;
+                    int iDI = 0, iDF = 0;
+                    if (doI && clj < ord) iDI = T.jk0[j] + clj + 1; /* offset 0, src/colloc.c:254 */
+                    if (doF) {
+                        const int k = clj - __ldg(T.seg_off[j] + T.nseg[j] - 1);
+                        if (k >= 0 && k < ord) iDF = T.jk0[j] + k + 1;
+                    }
+                    pp[7] = iDI | (iDF << 16);
+                }
+                sb += T.nseg[j] + 1;
+            }
+        }
+        cols_s[c] = use_sched ? __ldg(sched_cols + c) : c;
+    }
+
     const int ntiles = (P + GR - 1) / GR;
     const int tileC = GR * nC; /* doubles of coefficients per tile (contiguous in global memory) */
     auto stage_C = [&](int tile, int buf) {
@@ -228,6 +368,16 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
     };
     int buf = 0;
     if ((int)blockIdx.x < ntiles) stage_C(blockIdx.x, 0);
+#ifdef NTG_DBG_DELAY_NS
+    if (blockIdx.x >= gridDim.x / 2) {
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        do {
+            __nanosleep(500);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        } while (t1 - t0 < NTG_DBG_DELAY_NS);
+    }
+#endif
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
         const int p0 = tile * GR;
@@ -267,7 +417,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
 #pragma unroll
                     for (int d = 0; d < MD; d++) z[IZ + d] = ((mask >> d) & 1u) ? acc[d] : 0.0;
                     zp[j] = &z[IZ];
-                    if (A.Z != nullptr) {
+                    if (wantZ) {
 #pragma unroll
                         for (int d = 0; d < MD; d++)
                             A.Z[(size_t)p * T.nZ + T.iZ[j] + (size_t)bp * MD + d] = z[IZ + d];
@@ -297,12 +447,12 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                             double *cp = A.c + (size_t)p * T.ncnln + T.nnlic + bp;
 #pragma unroll
                             for (int m = 0; m < PK::kNnltc; m++) {
-                                if (A.c != nullptr) st_stream(cp + (size_t)m * nbps, cv[m]);
+                                if (want_c) st_stream(cp + (size_t)m * nbps, cv[m]);
                                 viol = fmax(viol, row_violation(cv[m], nl_bound(T, false, T.nnlic + m),
                                                                 nl_bound(T, true, T.nnlic + m)));
                             }
                         }
-                        if (wantJ) emit_rows_regs<PK, FULL, PK::kNnltc, 1>(T, A, Bt, offj, p, bp, dfc, T.nnlic);
+                        if (wantJ) emit_rows_regs<PK, FULL, PK::kNnltc, 1, false, HOT>(T, A, Bt, offj, p, bp, dfc, T.nnlic);
                     }
                 }
                 /* nonlinear initial constraints (breakpoint 0), src/constraints.c:88-117 */
@@ -324,11 +474,11 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                         if (con_v) {
 #pragma unroll
                             for (int m = 0; m < PK::kNnlic; m++) {
-                                if (A.c != nullptr) st_stream(A.c + (size_t)p * T.ncnln + m, cv[m]);
+                                if (want_c) st_stream(A.c + (size_t)p * T.ncnln + m, cv[m]);
                                 viol = fmax(viol, row_violation(cv[m], nl_bound(T, false, m), nl_bound(T, true, m)));
                             }
                         }
-                        if (wantJ) emit_rows_regs<PK, FULL, PK::kNnlic, 0>(T, A, Bt, offj, p, bp, dfc, 0);
+                        if (wantJ) emit_rows_regs<PK, FULL, PK::kNnlic, 0, false, HOT>(T, A, Bt, offj, p, bp, dfc, 0);
                     }
                 }
                 /* nonlinear final constraints (last breakpoint), src/constraints.c:165-195 */
@@ -351,15 +501,17 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                         if (con_v) {
 #pragma unroll
                             for (int m = 0; m < PK::kNnlfc; m++) {
-                                if (A.c != nullptr) st_stream(A.c + (size_t)p * T.ncnln + rb + m, cv[m]);
+                                if (want_c) st_stream(A.c + (size_t)p * T.ncnln + rb + m, cv[m]);
                                 viol = fmax(viol, row_violation(cv[m], nl_bound(T, false, T.nnlic + T.nnltc + m),
                                                                 nl_bound(T, true, T.nnlic + T.nnltc + m)));
                             }
                         }
-                        if (wantJ) emit_rows_regs<PK, FULL, PK::kNnlfc, 2>(T, A, Bt, offj, p, bp, dfc, rb);
+                        if (wantJ) emit_rows_regs<PK, FULL, PK::kNnlfc, 2, false, HOT>(T, A, Bt, offj, p, bp, dfc, rb);
                     }
                 }
-                if (viol > 0.0) atomicMax(&viol_s[plr], (unsigned long long)__double_as_longlong(viol));
+                /* per-breakpoint violation; phase B takes the maximum over the breakpoints (a maximum
+                 * does not depend on the order it is taken in) */
+                if (con_v) viol_s[bp * GRP + plr] = viol;
 
                 /* unintegrated (trajectory) cost, src/cost.c:99-132: the band of dIdC (chain rule
                  * through B) goes to shared memory for the quadrature */
@@ -376,7 +528,8 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                         if (obj_d) {
                             double *Dp = D_s + (size_t)bp * GRP + plr;
                             const int pitch = nbps * GRP;
-                            band_from_regs<PK, FULL>(T, Bt, df, [&](auto, int, double v) {
+                            cost_band<PK, FULL, PK::sp_ucf()>(T, Bt, df, [&](auto, auto, double v) {
+                                if ((NTG_DBG & 4) && v != 1.2345e300) return;
                                 *Dp = v;
                                 Dp += pitch;
                             });
@@ -396,7 +549,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                         cI_s[plr] = fv;
                         if (obj_d) {
                             double *Dp = DI_s + plr * S;
-                            band_from_regs<PK, FULL>(T, Bt, df, [&](auto, int, double v) { *Dp++ = v; });
+                            cost_band<PK, FULL, PK::sp_icf()>(T, Bt, df, [&](auto, auto, double v) { *Dp++ = v; });
                         }
                     }
                 }
@@ -413,7 +566,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                         cF_s[plr] = fv;
                         if (obj_d) {
                             double *Dp = DF_s + plr * S;
-                            band_from_regs<PK, FULL>(T, Bt, df, [&](auto, int, double v) { *Dp++ = v; });
+                            cost_band<PK, FULL, PK::sp_fcf()>(T, Bt, df, [&](auto, auto, double v) { *Dp++ = v; });
                         }
                     }
                 }
@@ -421,90 +574,83 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
         }
         __syncthreads();
 
-        /* ------- phase B: one chain per (problem, column); the scalar cost is one more column ------- */
-        const int items = GR * (nC + 1);
-        for (int q = threadIdx.x; q < items; q += blockDim.x) {
-            const int c = q / GR; /* column-major: a warp holds whole columns, its lanes walk the same runs */
-            const int plr = q - c * GR;
+        /* ------- phase B: one trapezoid chain per (problem, column); the scalar cost is column nC.
+         * Thread = (slot, problem lane); a slot walks the columns the schedule gave it, so that all
+         * slots carry the same number of terms and a warp's lanes run the same columns. ------- */
+        for (int plr = laneB; plr < GR && !(NTG_DBG & 1); plr += lanesB) {
             const int pb = p0 + plr;
-            if (pb >= P) continue;
-            if (c == nC) {
-                /* IntegrateVector TRAPEZOID, src/integrator.c:21-24; y = I + In + F, src/ntg.c:303,328 */
-                double In = 0.0;
-                if (doU && obj_v) {
-                    const double *fp = f_s + plr;
-                    double fprev = fp[0];
+            if (pb >= P) break;
+            for (int idx = it0; idx < it1; idx += istep) {
+                const int c = use_sched ? cols_s[idx] : idx;
+                if (c < nC && !want_g) continue;
+                const int *pp = par_s + c * 9;
+                const int i0 = pp[0], nend = pp[1], s0 = pp[2], cl = pp[6], ipk = pp[7];
+                const int *ss = segstart_s + pp[3], *so = segstart_s + pp[8];
+                const double *Dj = D_s + pp[4] + plr;
+                const unsigned order = (unsigned)pp[5];
+                bool run_chain = i0 < nend;
+                const double gI = (ipk & 0xffff) ? DI_s[plr * S + (ipk & 0xffff) - 1] : 0.0;
+                const double gF = (ipk >> 16) ? DF_s[plr * S + (ipk >> 16) - 1] : 0.0;
+                /* IntegrateVector / IntegrateFMatrixCols TRAPEZOID (src/integrator.c:21-24, :44-48 on
+                 * the matrix of src/cost.c:118-132): ascending breakpoint, run by run */
+                double gU = 0.0;
+                if (NTG_DBG & 16) run_chain = false;
+                if (run_chain) {
+                    int s = s0;
+                    int k = cl - so[s];
+                    double dcur = ((unsigned)k < order) ? Dj[(k * nbps + i0) * GRP] : 0.0;
+                    int n = i0 + 1;
+                    while (n <= nend) {
+                        int snext = ss[s + 1];
+                        if (n >= snext) {
+                            s++;
+                            k = cl - so[s];
+                            snext = ss[s + 1];
+                        }
+                        const int segend = snext - 1 < nend ? snext - 1 : nend;
+                        if ((unsigned)k < order) {
+                            const double *ptr = Dj + (size_t)(k * nbps + n) * GRP;
 #pragma unroll 4
-                    for (int i = 0; i < nbps - 1; i++) {
-                        const double fn = fp[(i + 1) * GRP];
-                        In = In + (dt_s[i] * (fn + fprev)) / 2;
-                        fprev = fn;
-                    }
-                }
-                const double y = (cI_s[plr] + In) + cF_s[plr];
-                if (obj_v && A.f != nullptr) A.f[pb] = y;
-                if (A.result != nullptr) {
-                    A.result[2 * (size_t)pb] = obj_v ? y : 0.0;
-                    A.result[2 * (size_t)pb + 1] = __longlong_as_double((long long)viol_s[plr]);
-                }
-                viol_s[plr] = 0ull; /* ready for the next tile */
-                continue;
-            }
-            if (!obj_d || A.g == nullptr) continue;
-            /* IntegrateFMatrixCols TRAPEZOID over the band (src/integrator.c:44-48 on the matrix of
-             * src/cost.c:118-132), ascending breakpoint; then Vector3Add, src/ntg.c:329 */
-            double gI = 0.0, gU = 0.0, gF = 0.0;
-            int segbase = 0;
-            static_for<0, NOUT>([&](auto jc) {
-                constexpr int j = decltype(jc)::value;
-                const int sb = segbase;
-                segbase += T.nseg[j] + 1;
-                const int cl = c - T.iC[j];
-                if (cl < 0 || cl >= T.ncoef[j]) return;
-                const unsigned order = FULL ? PK::kMaxOrd : T.order[j];
-                const int *ss = segstart_s + sb;
-                const int *so = segoff_s + sb;
-                const double *Dj = D_s + (size_t)T.jk0[j] * nbps * GRP + plr;
-                if (doU) {
-                    const int lo = __ldg(T.col_lo + c), hi = __ldg(T.col_hi + c);
-                    const int i0 = lo > 0 ? lo - 1 : 0;
-                    const int nend = (hi < nbps - 2 ? hi : nbps - 2) + 1;
-                    if (i0 < nend) {
-                        int s = __ldg(T.col_seg0 + c);
-                        int k = cl - so[s];
-                        double dcur = ((unsigned)k < order) ? Dj[(k * nbps + i0) * GRP] : 0.0;
-                        int n = i0 + 1;
-                        while (n <= nend) {
-                            int snext = ss[s + 1];
-                            if (n >= snext) {
-                                s++;
-                                k = cl - so[s];
-                                snext = ss[s + 1];
+                            for (; n <= segend; n++, ptr += GRP) {
+                                const double dn = *ptr;
+                                gU = gU + (dt_s[n - 1] * (dn + dcur)) / 2;
+                                dcur = dn;
                             }
-                            const int segend = snext - 1 < nend ? snext - 1 : nend;
-                            if ((unsigned)k < order) {
-                                const double *ptr = Dj + (size_t)(k * nbps + n) * GRP;
-#pragma unroll 4
-                                for (; n <= segend; n++, ptr += GRP) {
-                                    const double dn = *ptr;
-                                    gU = gU + (dt_s[n - 1] * (dn + dcur)) / 2;
-                                    dcur = dn;
-                                }
-                            } else { /* leaving the band: one term against an exact zero, the rest are zeros */
-                                gU = gU + (dt_s[n - 1] * (0.0 + dcur)) / 2;
-                                dcur = 0.0;
-                                n = segend + 1;
-                            }
+                        } else { /* leaving the band: one term against an exact zero, the rest are zeros */
+                            gU = gU + (dt_s[n - 1] * (0.0 + dcur)) / 2;
+                            dcur = 0.0;
+                            n = segend + 1;
                         }
                     }
                 }
-                if (doI && (unsigned)cl < order) gI = DI_s[plr * S + T.jk0[j] + cl]; /* offset 0, src/colloc.c:254 */
-                if (doF) {
-                    const int k = cl - so[T.nseg[j] - 1];
-                    if ((unsigned)k < order) gF = DF_s[plr * S + T.jk0[j] + k];
+                if ((NTG_DBG & 8) && gU != 1.2345e300) continue;
+                if (c < nC) {
+                    st_stream(A.g + (size_t)pb * nC + c, (gI + gU) + gF); /* Vector3Add, src/ntg.c:329 */
+                } else {
+                    const double y = (cI_s[plr] + gU) + cF_s[plr]; /* y = I + In + F, src/ntg.c:303,328 */
+                    if (HOT || (obj_v && A.f != nullptr)) A.f[pb] = y;
+                    if (A.result != nullptr) {
+                        A.result[2 * (size_t)pb] = obj_v ? y : 0.0;
+                        if (!con_v) A.result[2 * (size_t)pb + 1] = 0.0;
+                    }
                 }
-            });
-            st_stream(A.g + (size_t)pb * nC + c, (gI + gU) + gF);
+            }
+        }
+        /* maximum constraint violation per problem: four lanes per problem, then two shuffles */
+        if (con_v && A.result != nullptr) {
+            const int nv = GR * 4;
+            for (int base = 0; base < nv; base += blockDim.x) {
+                const int q = base + threadIdx.x;
+                const int plr = q >> 2, part = q & 3;
+                double vm = 0.0;
+                if (q < nv) {
+                    const double *vp = viol_s + plr;
+                    for (int i = part; i < nbps; i += 4) vm = fmax(vm, vp[i * GRP]);
+                }
+                vm = fmax(vm, __shfl_xor_sync(0xffffffffu, vm, 1));
+                vm = fmax(vm, __shfl_xor_sync(0xffffffffu, vm, 2));
+                if (q < nv && part == 0 && p0 + plr < P) A.result[2 * (size_t)(p0 + plr) + 1] = vm;
+            }
         }
         /* the barrier at the top of the next iteration separates this phase B from the next phase A */
     }
@@ -551,7 +697,11 @@ int launch_eval_small(const ntgb_launch *L)
     SmallSmem lay{G * R, nbps, T.S, T.nout, T.nC, segtot};
     const size_t smem = lay.bytes();
     if (smem > (size_t)L->max_smem_optin) return -1001;
-    auto kern = full ? ntg_eval_small_kernel<PK, true> : ntg_eval_small_kernel<PK, false>;
+    const ntgb_eval_args &a = L->args;
+    const bool hot = a.mode_obj == 2 && a.mode_con == 2 && a.jac_layout == NTGB_JAC_BAND && a.J != nullptr &&
+                     a.f != nullptr && a.g != nullptr && a.c != nullptr && a.Z == nullptr && T.ncnln > 0;
+    auto kern = full ? (hot ? ntg_eval_small_kernel<PK, true, true> : ntg_eval_small_kernel<PK, true, false>)
+                     : ntg_eval_small_kernel<PK, false, false>;
     int nb = 0;
     if (int rc = resident_blocks((const void *)kern, block, smem, L->max_smem_optin, &nb)) return rc;
     const int ntiles = (P + G * R - 1) / (G * R);

@@ -11,7 +11,7 @@
 
 #include <vector_types.h>
 
-#define NTGB_KERNEL_ABI 6
+#define NTGB_KERNEL_ABI 7
 #define NTGB_MAXOUT 8      /* outputs per problem the device tables can describe */
 #define NTGB_MAXORDER 20   /* PGS bsplvb work arrays: jmax = 20   */
 #define NTGB_MAXNLB 16     /* nonlinear bounds carried by value in the kernel params */
@@ -53,7 +53,17 @@ typedef struct ntgb_devtab {
     int plan_cwin;                  /* doubles of coefficients the widest CTA stages per problem */
     int plan_n;                     /* number of plan entries                                */
     double nl_lb_v[NTGB_MAXNLB], nl_ub_v[NTGB_MAXNLB];
+    /* quadrature schedule of the register-table kernel (K1s): the nC+1 trapezoid chains of a
+     * problem (column nC = the scalar cost) packed into NS slots of near-equal length, longest
+     * chain first, for a CTA of NTGB_SCHED_BLOCK threads working on sched_G*(r+1) problems per
+     * tile, r = 0..7.  Table r starts at sched + r*(NTGB_SCHED_BLOCK+1 + nC+1): slot starts
+     * [NTGB_SCHED_BLOCK+1] (into the column list), then the column list [nC+1]. */
+    int sched_G;
+    int sched_ns[8];
+    const int *sched;
 } ntgb_devtab;
+
+#define NTGB_SCHED_BLOCK 256
 
 /* cluster geometry of K1c for a horizon of nbps breakpoints (shared by core and launcher) */
 static inline void ntgb_cluster_geometry(int nbps, int *CL, int *bpc)

@@ -879,6 +879,7 @@ int ntgb_create(ntgb_problem **out, const ntgb_setup *s, int device)
             T.sched = dsched;
             T.sched_G = G0;
         }
+
     }
 
     /* do all outputs share one spline setup (one table serves all)? */

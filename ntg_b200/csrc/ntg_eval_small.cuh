@@ -53,20 +53,27 @@ __host__ __device__ constexpr int pk_tab_doubles() { return pk_tab_base<PK>(PK::
 
 struct SmallSmem {
     int GR, nbps, S, nout, nC, segtot;
-    /* problem index is the FASTEST dimension of D and f (odd pitch GRP): phase A lanes are
-     * consecutive breakpoints (stride GRP doubles, conflict-free because GRP is odd), phase B
-     * lanes are consecutive problems of one column (stride 1) */
-    __host__ __device__ int GRP() const { return GR | 1; }
-    __host__ __device__ size_t D_off() const { return 0; }                                    /* [S][nbps][GRP] */
-    __host__ __device__ size_t f_off() const { return (size_t)S * nbps * GRP(); }             /* [nbps][GRP]    */
-    __host__ __device__ size_t DI_off() const { return f_off() + (size_t)nbps * GRP(); }      /* [GR][S]        */
-    __host__ __device__ size_t DF_off() const { return DI_off() + (size_t)GR * S; }           /* [GR][S]        */
-    __host__ __device__ size_t cI_off() const { return DF_off() + (size_t)GR * S; }           /* [GR]           */
-    __host__ __device__ size_t cF_off() const { return cI_off() + GR; }                       /* [GR]           */
-    __host__ __device__ size_t viol_off() const { return cF_off() + GR; }                     /* [nbps][GRP]    */
-    __host__ __device__ size_t dt_off() const { return viol_off() + (size_t)nbps * GRP(); }   /* [nbps]         */
-    __host__ __device__ size_t C_off() const { return dt_off() + nbps; }                      /* [2][GR*nC]     */
-    __host__ __device__ size_t seg_off() const { return C_off() + 2 * (size_t)GR * nC; }      /* int [2][segtot] */
+    /* D, f and viol hold one ROW of `pitch` doubles per (band slot, problem): phase A lanes are
+     * consecutive breakpoints of one row (stride 1), phase B lanes are consecutive problems (stride
+     * pitch) and a chain walks its row with 16-byte loads.  pitch is even with pitch/2 odd, so the
+     * eight lanes of a quarter-warp hit eight different 16-byte bank groups. */
+    __host__ __device__ int pitch() const
+    {
+        int p = (nbps + 1) & ~1;
+        if (((p >> 1) & 1) == 0) p += 2;
+        return p;
+    }
+    __host__ __device__ static size_t even(size_t n) { return (n + 1) & ~(size_t)1; }
+    __host__ __device__ size_t D_off() const { return 0; }                                         /* [S][GR][pitch] */
+    __host__ __device__ size_t f_off() const { return (size_t)S * GR * pitch(); }                  /* [GR][pitch]    */
+    __host__ __device__ size_t viol_off() const { return f_off() + (size_t)GR * pitch(); }         /* [GR][pitch]    */
+    __host__ __device__ size_t DI_off() const { return viol_off() + (size_t)GR * pitch(); }        /* [GR][S]        */
+    __host__ __device__ size_t DF_off() const { return DI_off() + even((size_t)GR * S); }          /* [GR][S]        */
+    __host__ __device__ size_t cI_off() const { return DF_off() + even((size_t)GR * S); }          /* [GR]           */
+    __host__ __device__ size_t cF_off() const { return cI_off() + even(GR); }                      /* [GR]           */
+    __host__ __device__ size_t dt_off() const { return cF_off() + even(GR); }                      /* wt, Wf: [2][pitch + 2] */
+    __host__ __device__ size_t C_off() const { return dt_off() + 2 * (size_t)(pitch() + 2); }      /* [2][GR*nC]     */
+    __host__ __device__ size_t seg_off() const { return C_off() + 2 * even((size_t)GR * nC); }     /* ints, see the kernel */
     __host__ __device__ size_t bytes() const { return seg_off() * 8 + (2 * (size_t)segtot + 4 + (size_t)(nC + 1) * 10) * 4 + 8; }
 };
 
@@ -133,6 +140,61 @@ __device__ __forceinline__ double nl_bound(const ntgb_devtab &T, bool upper, int
 {
     if (T.nl_inline) return upper ? T.nl_ub_v[idx] : T.nl_lb_v[idx];
     return __ldg((upper ? T.nl_ub : T.nl_lb) + idx);
+}
+
+/* Trapezoid quadrature of one run of a band row (src/integrator.c:21-24, :44-48).  row[n] is the
+ * band value at breakpoint n (16-byte aligned at even n), wt[n] = (t[n]-t[n-1])/2.
+ *
+ * trap_run_exact: terms n0..n1, g = g + wt[n]*(row[n] + row[n-1]) one after the other in ascending
+ * order -- the reference's operation order ((dt*(a+b))/2 with the exact halving moved into the
+ * weight: identical bits unless a term underflows below 2.2e-308).  The terms do not depend on the
+ * running sum, so they are computed four at a time ahead of the additions. */
+__device__ __forceinline__ void trap_run_exact(const double *row, const double *wt, int n0, int n1, double &prev,
+                                               double &g)
+{
+    int n = n0;
+    if ((n & 1) && n <= n1) {
+        const double d = row[n];
+        g = g + wt[n] * (d + prev);
+        prev = d;
+        n++;
+    }
+    for (; n + 3 <= n1; n += 4) {
+        const double2 d01 = *reinterpret_cast<const double2 *>(row + n), d23 = *reinterpret_cast<const double2 *>(row + n + 2);
+        const double2 w01 = *reinterpret_cast<const double2 *>(wt + n), w23 = *reinterpret_cast<const double2 *>(wt + n + 2);
+        const double t0 = w01.x * (d01.x + prev), t1 = w01.y * (d01.y + d01.x), t2 = w23.x * (d23.x + d01.y),
+                     t3 = w23.y * (d23.y + d23.x);
+        g = g + t0;
+        g = g + t1;
+        g = g + t2;
+        g = g + t3;
+        prev = d23.y;
+    }
+    for (; n <= n1; n++) {
+        const double d = row[n];
+        g = g + wt[n] * (d + prev);
+        prev = d;
+    }
+}
+
+/* fast variant: the same integral as node weights, sum_n Wf[n]*row[n] with Wf[n] = wt[n] + wt[n+1]
+ * (the band is zero at both ends of a column's support, so no end corrections), four partial sums */
+__device__ __forceinline__ void trap_run_fast(const double *row, const double *Wf, int n0, int n1, double (&g)[4])
+{
+    int n = n0;
+    if ((n & 1) && n <= n1) {
+        g[0] = g[0] + Wf[n] * row[n];
+        n++;
+    }
+    for (; n + 3 <= n1; n += 4) {
+        const double2 d01 = *reinterpret_cast<const double2 *>(row + n), d23 = *reinterpret_cast<const double2 *>(row + n + 2);
+        const double2 w01 = *reinterpret_cast<const double2 *>(Wf + n), w23 = *reinterpret_cast<const double2 *>(Wf + n + 2);
+        g[0] = g[0] + w01.x * d01.x;
+        g[1] = g[1] + w01.y * d01.y;
+        g[2] = g[2] + w23.x * d23.x;
+        g[3] = g[3] + w23.y * d23.y;
+    }
+    for (; n <= n1; n++) g[0] = g[0] + Wf[n] * row[n];
 }
 
 /* constraint rows of one kind evaluated at this thread's breakpoint:
@@ -223,7 +285,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
     extern __shared__ double smem[];
     const int GR = G * R;
     const SmallSmem L{GR, T.nbps, T.S, T.nout, T.nC, segtot};
-    const int nbps = T.nbps, GRP = L.GRP(), nC = T.nC, P = A.P, S = T.S;
+    const int nbps = T.nbps, pitch = L.pitch(), nC = T.nC, P = A.P, S = T.S;
     double *D_s = smem + L.D_off();
     double *f_s = smem + L.f_off();
     double *DI_s = smem + L.DI_off();
@@ -231,7 +293,8 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
     double *cI_s = smem + L.cI_off();
     double *cF_s = smem + L.cF_off();
     double *viol_s = smem + L.viol_off();
-    double *dt_s = smem + L.dt_off();
+    double *wt_s = smem + L.dt_off();  /* wt[n] = (t[n]-t[n-1])/2, wt[0] = 0 */
+    double *Wf_s = wt_s + pitch + 2;   /* node weights wt[n] + wt[n+1] */
     double *C_s = smem + L.C_off();
     int *segstart_s = reinterpret_cast<int *>(smem + L.seg_off());
     int *segoff_s = segstart_s + segtot;
@@ -256,7 +319,12 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
     const bool want_c = HOT || A.c != nullptr;
 
     /* ---- once per CTA: dt, offset runs, accumulators; once per thread: its table slice ---- */
-    for (int i = threadIdx.x; i < nbps - 1; i += blockDim.x) dt_s[i] = __ldg(T.bps + i + 1) - __ldg(T.bps + i);
+    for (int n = threadIdx.x; n < pitch + 2; n += blockDim.x) {
+        const double lo = (n >= 1 && n < nbps) ? (__ldg(T.bps + n) - __ldg(T.bps + n - 1)) * 0.5 : 0.0;
+        const double hi = (n + 1 < nbps) ? (__ldg(T.bps + n + 1) - __ldg(T.bps + n)) * 0.5 : 0.0;
+        wt_s[n] = lo;
+        Wf_s[n] = lo + hi;
+    }
     {
         int base = 0;
         for (int j = 0; j < T.nout; j++) {
@@ -323,7 +391,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
         int *pp = par_s + c * 9;
         if (c == nC) {
             pp[0] = 0; pp[1] = (doU && obj_v) ? nbps - 1 : 0; pp[2] = 0; pp[3] = 2 * segtot; pp[8] = 2 * segtot + 2;
-            pp[4] = S * nbps * GRP; /* f_s follows D_s */
+            pp[4] = S * GR * pitch; /* f_s follows D_s */
             pp[5] = 1; pp[6] = 0; pp[7] = 0;
         } else {
             int sb = 0;
@@ -340,7 +408,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                     }
                     pp[3] = sb;
                     pp[8] = segtot + sb;
-                    pp[4] = T.jk0[j] * nbps * GRP;
+                    pp[4] = T.jk0[j] * GR * pitch;
                     pp[5] = ord;
                     pp[6] = clj;
                     int iDI = 0, iDF = 0;
@@ -368,16 +436,6 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
     };
     int buf = 0;
     if ((int)blockIdx.x < ntiles) stage_C(blockIdx.x, 0);
-#ifdef NTG_DBG_DELAY_NS
-    if (blockIdx.x >= gridDim.x / 2) {
-        unsigned long long t0, t1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        do {
-            __nanosleep(500);
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        } while (t1 - t0 < NTG_DBG_DELAY_NS);
-    }
-#endif
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
         const int p0 = tile * GR;
@@ -511,7 +569,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                 }
                 /* per-breakpoint violation; phase B takes the maximum over the breakpoints (a maximum
                  * does not depend on the order it is taken in) */
-                if (con_v) viol_s[bp * GRP + plr] = viol;
+                if (con_v) viol_s[plr * pitch + bp] = viol;
 
                 /* unintegrated (trajectory) cost, src/cost.c:99-132: the band of dIdC (chain rule
                  * through B) goes to shared memory for the quadrature */
@@ -524,14 +582,14 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                         int mode = mode_obj, i = bp;
                         PK::cb_ucf(&mode, &nstate, &i, &fv, df, zp);
                         note_abort(A, mode);
-                        f_s[bp * GRP + plr] = fv;
+                        f_s[plr * pitch + bp] = fv;
                         if (obj_d) {
-                            double *Dp = D_s + (size_t)bp * GRP + plr;
-                            const int pitch = nbps * GRP;
+                            double *Dp = D_s + (size_t)plr * pitch + bp;
+                            const int slot_pitch = GR * pitch;
                             cost_band<PK, FULL, PK::sp_ucf()>(T, Bt, df, [&](auto, auto, double v) {
                                 if ((NTG_DBG & 4) && v != 1.2345e300) return;
                                 *Dp = v;
-                                Dp += pitch;
+                                Dp += slot_pitch;
                             });
                         }
                     }
@@ -586,7 +644,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                 const int *pp = par_s + c * 9;
                 const int i0 = pp[0], nend = pp[1], s0 = pp[2], cl = pp[6], ipk = pp[7];
                 const int *ss = segstart_s + pp[3], *so = segstart_s + pp[8];
-                const double *Dj = D_s + pp[4] + plr;
+                const double *Dj = D_s + pp[4] + (size_t)plr * pitch; /* row of band slot k: Dj + k*GR*pitch */
                 const unsigned order = (unsigned)pp[5];
                 bool run_chain = i0 < nend;
                 const double gI = (ipk & 0xffff) ? DI_s[plr * S + (ipk & 0xffff) - 1] : 0.0;
@@ -596,31 +654,43 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                 double gU = 0.0;
                 if (NTG_DBG & 16) run_chain = false;
                 if (run_chain) {
+                    const int rowp = GR * pitch;
                     int s = s0;
                     int k = cl - so[s];
-                    double dcur = ((unsigned)k < order) ? Dj[(k * nbps + i0) * GRP] : 0.0;
-                    int n = i0 + 1;
-                    while (n <= nend) {
-                        int snext = ss[s + 1];
-                        if (n >= snext) {
-                            s++;
-                            k = cl - so[s];
-                            snext = ss[s + 1];
-                        }
-                        const int segend = snext - 1 < nend ? snext - 1 : nend;
-                        if ((unsigned)k < order) {
-                            const double *ptr = Dj + (size_t)(k * nbps + n) * GRP;
-#pragma unroll 4
-                            for (; n <= segend; n++, ptr += GRP) {
-                                const double dn = *ptr;
-                                gU = gU + (dt_s[n - 1] * (dn + dcur)) / 2;
-                                dcur = dn;
+                    if constexpr (PK::kExact) {
+                        double dcur = ((unsigned)k < order) ? Dj[(size_t)k * rowp + i0] : 0.0;
+                        int n = i0 + 1;
+                        while (n <= nend) {
+                            int snext = ss[s + 1];
+                            if (n >= snext) {
+                                s++;
+                                k = cl - so[s];
+                                snext = ss[s + 1];
                             }
-                        } else { /* leaving the band: one term against an exact zero, the rest are zeros */
-                            gU = gU + (dt_s[n - 1] * (0.0 + dcur)) / 2;
-                            dcur = 0.0;
+                            const int segend = snext - 1 < nend ? snext - 1 : nend;
+                            if ((unsigned)k < order) {
+                                trap_run_exact(Dj + (size_t)k * rowp, wt_s, n, segend, dcur, gU);
+                            } else { /* leaving the band: one term against an exact zero, the rest are zeros */
+                                gU = gU + wt_s[n] * (0.0 + dcur);
+                                dcur = 0.0;
+                            }
                             n = segend + 1;
                         }
+                    } else {
+                        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+                        int n = i0;
+                        while (n <= nend) {
+                            int snext = ss[s + 1];
+                            if (n >= snext) {
+                                s++;
+                                k = cl - so[s];
+                                snext = ss[s + 1];
+                            }
+                            const int segend = snext - 1 < nend ? snext - 1 : nend;
+                            if ((unsigned)k < order) trap_run_fast(Dj + (size_t)k * rowp, Wf_s, n, segend, acc);
+                            n = segend + 1;
+                        }
+                        gU = (acc[0] + acc[1]) + (acc[2] + acc[3]);
                     }
                 }
                 if ((NTG_DBG & 8) && gU != 1.2345e300) continue;
@@ -636,19 +706,26 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                 }
             }
         }
-        /* maximum constraint violation per problem: four lanes per problem, then two shuffles */
+        /* maximum constraint violation per problem: eight lanes per problem, then three shuffles */
         if (con_v && A.result != nullptr) {
-            const int nv = GR * 4;
+            const int nv = GR * 8;
             for (int base = 0; base < nv; base += blockDim.x) {
                 const int q = base + threadIdx.x;
-                const int plr = q >> 2, part = q & 3;
-                double vm = 0.0;
+                const int plr = q >> 3, part = q & 7;
+                double vm = 0.0, vn = 0.0;
                 if (q < nv) {
-                    const double *vp = viol_s + plr;
-                    for (int i = part; i < nbps; i += 4) vm = fmax(vm, vp[i * GRP]);
+                    const double *vp = viol_s + (size_t)plr * pitch;
+                    int i = part;
+                    for (; i + 8 < nbps; i += 16) {
+                        vm = fmax(vm, vp[i]);
+                        vn = fmax(vn, vp[i + 8]);
+                    }
+                    if (i < nbps) vm = fmax(vm, vp[i]);
                 }
+                vm = fmax(vm, vn);
                 vm = fmax(vm, __shfl_xor_sync(0xffffffffu, vm, 1));
                 vm = fmax(vm, __shfl_xor_sync(0xffffffffu, vm, 2));
+                vm = fmax(vm, __shfl_xor_sync(0xffffffffu, vm, 4));
                 if (q < nv && part == 0 && p0 + plr < P) A.result[2 * (size_t)(p0 + plr) + 1] = vm;
             }
         }

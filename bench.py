@@ -470,7 +470,7 @@ def main():
         bytes_launch = P * spec.bytes_per_eval()
         ach = bytes_launch / (ms_kernel * 1e-3) / 1e9
         cfgd = workload_config(a.workload, spec, P, world)
-        cfgd["variant"] = ("fast (FMA contraction allowed)" if fast else
+        cfgd["variant"] = ("fast (FMA contraction, node-weight quadrature with 4 partial sums)" if fast else
                            "exact (-fmad=false, reference summation order, bit-identical to the CPU reference)")
         cfgd["l2"] = (f"inputs+outputs of one step = {r['footprint_mb']:.0f} MB over a ring of {r['nset']} "
                       f"buffer set(s), larger than the 126 MB L2")

@@ -200,7 +200,7 @@ __device__ __forceinline__ void trap_run_fast(const double *row, const double *W
 /* constraint rows of one kind evaluated at this thread's breakpoint:
  * KIND 0 initial (columns from iC_j, src/colloc.c:254), 1 trajectory, 2 final.
  * BAND selects the layout at compile time; SPARSE uses the pack's probed sparsity masks. */
-template <class PK, bool FULL, int NCON, int KIND, bool ONE, bool BAND, bool SPARSE>
+template <class PK, bool FULL, int NCON, int KIND, bool ONE, bool BAND, bool SPARSE, int MOFF = 0>
 __device__ __forceinline__ void emit_rows_layout(const ntgb_devtab &T, const ntgb_eval_args &A, const double *Bt,
                                                  const int *offj, int p, int bp,
                                                  const double (&dfc)[NCON][pk_nz<PK>()], int row_base)
@@ -214,7 +214,7 @@ __device__ __forceinline__ void emit_rows_layout(const ntgb_devtab &T, const ntg
         const unsigned stride8 = (KIND == 1 ? (unsigned)nbps : 1u) * 8u;
         static_for<0, NCON>([&](auto mc) {
             constexpr int m = decltype(mc)::value;
-            constexpr unsigned long long MASK = SPARSE ? sp_con<PK, KIND>(m) : kDense;
+            constexpr unsigned long long MASK = SPARSE ? sp_con<PK, KIND>(MOFF + m) : kDense;
             if constexpr (FULL) {
                 constexpr int SF = PK::kNout * PK::kMaxOrd;
                 band_from_regs<PK, FULL, ONE, MASK>(T, Bt, dfc[m], [&](auto jc, auto kc, double v) {
@@ -234,7 +234,7 @@ __device__ __forceinline__ void emit_rows_layout(const ntgb_devtab &T, const ntg
         double *Jp = A.J + (size_t)p * T.ncnln * T.nC;
         static_for<0, NCON>([&](auto mc) {
             constexpr int m = decltype(mc)::value;
-            constexpr unsigned long long MASK = SPARSE ? sp_con<PK, KIND>(m) : kDense;
+            constexpr unsigned long long MASK = SPARSE ? sp_con<PK, KIND>(MOFF + m) : kDense;
             const int row = (KIND == 1) ? row_base + m * nbps + bp : row_base + m;
             band_from_regs<PK, FULL, ONE, MASK>(T, Bt, dfc[m], [&](auto jc, auto kc, double v) {
                 constexpr int j = decltype(jc)::value;

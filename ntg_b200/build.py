@@ -344,6 +344,8 @@ def repo_packs() -> List[PackManifest]:
                      {"nlicf": "2", "nltcf": "3", "nlfcf": "1"}),
         PackManifest("hi20", os.path.join(P, "hi20.c"), ["3"], "20",
                      {"ucf": "hi20_ucf", "nltcf": "hi20_nltcf"}, {"nltcf": "1"}),
+        PackManifest("cond", os.path.join(P, "cond.c"), ["3", "3"], "4",
+                     {"ucf": "cond_ucf", "nltcf": "cond_nltcf"}, {"nltcf": "2"}),
     ]
     out: List[PackManifest] = []
     for m in packs:

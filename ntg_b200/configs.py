@@ -102,6 +102,16 @@ def high_order(order: int = 20, mult: int = 3, ninterv: int = 4, nbps: int = 33,
         trajectorycostav=av, trajectoryconstrav=av, lowerb=np.array([-1.0]), upperb=np.array([1.0]))
 
 
+def conditional(nbps: int = 32, name: str = "test_cond") -> ProblemSpec:
+    """Test-only: callbacks whose derivative sparsity depends on the data (packs/cond.c)."""
+    av = [(j, d) for j in range(2) for d in range(3)]
+    return ProblemSpec(
+        name=name, pack="cond", order=[4, 4], mult=[2, 2], maxderiv=[3, 3], ninterv=[3, 3], nbps=nbps,
+        t0=0.0, t1=1.0, callbacks={"ucf": "cond_ucf", "nltcf": "cond_nltcf"}, nucf=1, nnltc=2,
+        trajectorycostav=av, trajectoryconstrav=av,
+        lowerb=np.array([-1.0, -1.0]), upperb=np.array([1.0, 1.0]))
+
+
 # BASELINE.json configs -> (spec factory, batch size, coefficient sampler)
 def coefficients(cfg: str, P: int, spec: ProblemSpec, seed: int | None = None) -> np.ndarray:
     """Synthetic coefficient batches, seeds and ranges of SURVEY.md section 8(d)."""

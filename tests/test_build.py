@@ -55,3 +55,28 @@ def test_reference_examples_compile_unmodified():
         so = build.build_pack(m)
         lib = C.CDLL(so)
         assert hasattr(lib, m.rename_main)
+
+
+def test_sparsity_probe_masks():
+    """probe_sparsity(): bit iz_j + l of a row's mask is set iff the callback ever produced a
+    non-zero there at the probe points.  kincar (packs/kincar.c): the cost touches only the two
+    second derivatives; cond.c hides two entries behind |z| > 50 that the probe cannot see -- the
+    kernels' run-time check covers those (tests/test_gpu_parity.py)."""
+    by = {m.name: m for m in build.repo_packs()}
+    k = build.probe_sparsity(by["kincar"])
+    assert k["ucf"] == [0b100100]
+    assert k["nltcf"] == [0b010010, 0b110110]
+    c = build.probe_sparsity(by["cond"])
+    assert c["ucf"] == [0b100010] and c["nltcf"] == [0b000010, 0b100001]
+    e = build.probe_sparsity(by["endpt"])
+    assert set(e) == {"icf", "ucf", "fcf", "nlicf", "nltcf", "nlfcf"} and len(e["nltcf"]) == 3
+    w = open(build.generate_wrapper(by["kincar"])).read()
+    assert "sp_ucf() { return 0x24ull; }" in w and "0x12ull, 0x36ull" in w
+
+
+def test_sparsity_probe_failure_means_dense(tmp_path):
+    """a file the probe cannot compile must leave every mask dense (all ones), never fail the build"""
+    src = tmp_path / "broken.c"
+    src.write_text("void f(int *mode,int *nstate,int *i,double *f,double *df,double **zp) { this is not C }\n")
+    m = build.PackManifest("t_broken", str(src), ["2"], "3", {"ucf": "f"})
+    assert build.probe_sparsity(m) == {}

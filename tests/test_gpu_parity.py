@@ -481,3 +481,27 @@ def test_empty_batch_is_a_no_op(torch_cuda):
     torch.cuda.synchronize()
     assert float(out["f"].abs().sum()) == 0.0
     pb.close()
+
+
+@pytest.mark.parametrize("fast", [False, True], ids=["exact", "fast"])
+def test_data_dependent_sparsity_falls_back_to_dense(torch_cuda, port, fast):
+    """The build-time probe declares derivative entries that packs/cond.c writes only for |z| > 50
+    structurally zero (checked in tests/test_build.py); coefficients that reach those branches must
+    still give the reference's results: the kernel verifies the probed zeros at every evaluation and
+    takes the dense chain rule when one of them is not +0.0."""
+    spec = configs.conditional()
+    rng = np.random.default_rng(4242)
+    X = rng.uniform(-2.0, 2.0, (96, spec.nC))
+    X[32:64] = rng.uniform(-120.0, 120.0, (32, spec.nC))      # both conditional branches fire
+    X[64:] = rng.uniform(40.0, 60.0, (32, spec.nC))           # around the threshold: mixed within a warp
+    o = port.eval(spec, X, dense=False, band=True)
+    zfired = (X[32:64].max() > 50.0) and (X[32:64].min() < -50.0)
+    assert zfired
+    pb, r = gpu_eval(torch_cuda, spec, X, fast)
+    cmp = assert_close if fast else assert_bitexact
+    for k in ("f", "g", "c", "Jband"):
+        cmp(r[k], o[k], f"conditional sparsity ({'fast' if fast else 'exact'}): {k}")
+    # the conditional entries really are non-zero somewhere (otherwise this test proves nothing)
+    J = o["Jband"]
+    assert np.count_nonzero(o["g"]) > 0 and np.isfinite(J).all()
+    pb.close()

@@ -208,7 +208,7 @@ def run_reference_arm(a):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     return 0
 
 
@@ -390,6 +390,26 @@ def time_e2e(torch, pb, spec, cfg, P, steps, warmup, full: bool):
                      "(objective, violation) table to host; g, c, J computed and left resident in HBM")}
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version
+    banner on stdout when NCCL_DEBUG is set), so file descriptor 1 is pointed at stderr for the run
+    and the line goes to the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -403,6 +423,7 @@ def main():
     ap.add_argument("--ref-step-seconds", type=float, default=1.0)
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
+    _quiet_stdout()
 
     if a.impl == "reference":
         return run_reference_arm(a)
@@ -492,7 +513,7 @@ def main():
                 pass
         if world == 1 and not a.no_others:
             line["cpu_baseline"] = cpu_baseline(a.workload)
-        print(json.dumps(line), flush=True)
+        _emit(line)
     pb.close()
     if dist is not None:
         dist.barrier()

@@ -43,12 +43,14 @@ typedef struct MatrixStruct {
  * initialguess is overwritten with the solution (src/ntg.c:109).  Solving
  * needs NPSOL's npsol_/npoptn_ to be present in the process (they are looked
  * up at run time; NPSOL is separately licensed and never bundled).  If they
- * are absent, a problem with no nonlinear constraints and only equality linear
- * constraints (the class of both shipped examples) is solved by the library's
- * own reduced-space BFGS (ntgb_solve_eq; *inform = 0 / 1 / 4 with NPSOL's
- * meaning, istate / clambda / R untouched, a notice on stderr; switch off with
- * NTG_B200_NO_BUILTIN_SOLVER=1); for any other problem *inform is set to
- * NTG_INFORM_NO_NPSOL and nothing is solved.
+ * are absent the library's own solvers stand in: a problem with no nonlinear
+ * constraints and only equality linear constraints (the class of both shipped
+ * examples) goes to the reduced-space BFGS (ntgb_solve_eq), any other to the
+ * augmented-Lagrangian driver (ntgb_solve_nlp); *inform = 0 / 1 / 4 / 6 with
+ * NPSOL's meaning, istate / clambda / R untouched, a notice on stderr.  With
+ * NTG_B200_NO_BUILTIN_SOLVER=1, or when the problem exceeds the solvers' limit
+ * of 32 free directions, *inform is set to NTG_INFORM_NO_NPSOL and nothing is
+ * solved.
  */
 void ntg(int nout, double *bps, int nbps, int *kninterv, double **knots,
          int *order, int *mult, int *max_deriv,

@@ -235,6 +235,33 @@ typedef struct ntgb_solve_opts {
 int  ntgb_solve_eq(ntgb_problem *pb, int P, double *C, double *f, int *iters, int *status,
                    const ntgb_solve_opts *opts, void *stream);
 
+/*
+ * Batched solve of the GENERAL problem ntg() poses (src/ntg.c:162-253): linear equalities are
+ * eliminated as in ntgb_solve_eq; linear inequalities and the nonlinear constraints
+ * bl <= c(C) <= bu go into an augmented Lagrangian (Powell-Hestenes-Rockafellar form for two-sided
+ * bounds) that is minimised per problem by the same reduced-space BFGS, multipliers and penalty
+ * updated between rounds.  Every step is a batched kernel: evaluation with the band Jacobian,
+ * multiplier / merit kernel, J^T*mu gather per gradient column, BFGS direction, batched Armijo line
+ * search on the augmented Lagrangian.  C [P][nC] (device): guesses in, solutions out.  f, viol
+ * (maximum violation of any constraint), iters (evaluations of the inner loop), status
+ * (1 = violation <= ctol and reduced gradient <= gtol, 2 = violation <= ctol and no further
+ * decrease of the merit function possible, 0 = not converged) are optional device outputs.
+ * Synchronous.  A local method with no globalisation beyond the line search: it returns a KKT
+ * point near the guess, like the SQP solver it stands in for.
+ */
+typedef struct ntgb_nlp_opts {
+    int max_outer;    /* multiplier updates, default 40 */
+    int max_inner;    /* BFGS iterations per round, default 80 */
+    double gtol;      /* reduced gradient of the augmented Lagrangian, relative to max(1,|L|); default 1e-6 */
+    double ctol;      /* constraint violation, relative to max(1, |bound|); default 1e-6 */
+    double rho0;      /* initial penalty, default 10 */
+    double rho_mul;   /* penalty growth when the violation does not drop by 4x, default 10 */
+    double c1;        /* Armijo constant, default 1e-4 */
+    int check_every;  /* host reads the done counter every this many inner iterations, default 4 */
+} ntgb_nlp_opts;
+int  ntgb_solve_nlp(ntgb_problem *pb, int P, double *C, double *f, double *viol, int *iters, int *status,
+                    const ntgb_nlp_opts *opts, void *stream);
+
 /* ---- callback packs ------------------------------------------------------ */
 /*
  * A pack is a shared object produced by tools/ntg_pack.py from a user's

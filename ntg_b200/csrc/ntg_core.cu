@@ -125,6 +125,19 @@ struct ntgb_problem {
         double *blob = nullptr;
         int *iblob = nullptr;
     } red;
+    /* ntgb_solve_nlp: equality rows eliminated (own N / Cpart), the other linear rows kept as
+     * general constraints next to the nonlinear ones */
+    struct {
+        bool ready = false;
+        int nr = 0, n_li = 0, m = 0;
+        double *N = nullptr, *Cpart = nullptr;
+        int *li_idx = nullptr;      /* [n_li] linear row of general constraint i */
+        double *hl = nullptr, *hu = nullptr; /* [m] bounds: linear inequality rows, then the nonlinear rows */
+        double *A = nullptr;        /* dense nclin x nC, column-major (for A_in^T mu) */
+        size_t cap = 0, capt = 0;
+        double *blob = nullptr, *tblob = nullptr;
+        int *iblob = nullptr;
+    } alm;
     /* scratch of ntgb_linesearch: trial coefficients, result table, linear violation */
     struct { size_t n = 0; double *Ct = nullptr, *res = nullptr, *lv = nullptr; } ls;
 };
@@ -328,7 +341,8 @@ __global__ void k_solve_init(int P, int nC, int nr, const double *N, const doubl
     state[p] = 0;
     iters[p] = 0;
     fails[p] = -1; /* -1 no previous step, 1 last step failed (both: H = I, steepest descent);
-                      2 previous step exists and H is still the identity; 0 normal */
+                      2 previous step exists and H is still the identity; 0 normal;
+                      -2 no previous step but H carries over (set by the augmented-Lagrangian driver) */
 }
 
 /* reduced gradient, convergence test, BFGS update of the inverse Hessian, search direction */
@@ -532,6 +546,134 @@ int reduce_linear(const std::vector<double> &A, int m, int n, const std::vector<
     return 0;
 }
 
+/* ---- ntgb_solve_nlp: augmented Lagrangian on top of the reduced-space BFGS kernels above ----
+ * general constraints h = [A_in*C ; c(C)], bounds hl <= h <= hu, multipliers lam, penalty rho.
+ * PHR form: t = h + lam/rho, p = clamp(t, hl, hu), mu = rho*(t - p),
+ *           L_A = f + sum( rho/2*(t-p)^2 - lam^2/(2 rho) ),  grad L_A = g + dh^T mu. */
+__device__ __forceinline__ double alm_row(double h, double lam, double rho, double lo, double hi, double &mu,
+                                          double &viol)
+{
+    const double t = h + lam / rho;
+    const double pr = t < lo ? lo : (t > hi ? hi : t);
+    mu = rho * (t - pr);
+    double v = 0.0;
+    if (lo - h > v) v = lo - h;
+    if (h - hi > v) v = h - hi;
+    const double sc = fmax(1.0, fmax(fabs(lo) < 1e19 ? fabs(lo) : 0.0, fabs(hi) < 1e19 ? fabs(hi) : 0.0));
+    viol = v / sc;
+    return 0.5 * rho * (t - pr) * (t - pr) - 0.5 * lam * lam / rho;
+}
+
+/* one warp per evaluation point q (a problem, or a line-search trial of problem q / nalpha):
+ * multipliers (optional), augmented Lagrangian value, scaled violation */
+__global__ void k_alm_mu(int Q, int nalpha, int ncnln, int nclin, int n_li, const int *li_idx, const double *hl,
+                         const double *hu, const double *lam, const double *rho, const double *f, const double *c,
+                         const double *lin, double *mu, double *LA, double *viol, int LAstride)
+{
+    const int q = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= Q) return;
+    const int p = q / nalpha;
+    const int m = n_li + ncnln;
+    const double r = rho[p];
+    double acc = 0.0, vmax = 0.0;
+    for (int i = lane; i < m; i += 32) {
+        const double h = i < n_li ? lin[(size_t)q * nclin + li_idx[i]] : c[(size_t)q * ncnln + (i - n_li)];
+        double mui, vi;
+        acc += alm_row(h, lam[(size_t)p * m + i], r, hl[i], hu[i], mui, vi);
+        vmax = fmax(vmax, vi);
+        if (mu != nullptr) mu[(size_t)q * m + i] = mui;
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
+    }
+    if (lane == 0) {
+        LA[(size_t)q * LAstride] = f[q] + acc;
+        if (viol != nullptr) viol[q] = vmax;
+    }
+}
+
+/* gradient of the augmented Lagrangian, one thread per (problem, column): g + J^T mu_nl + A_in^T mu_li,
+ * J in band layout (include/ntg_b200.h, NTGB_JAC_BAND) gathered over the column's support */
+__global__ void k_alm_grad(int P, ntgb_devtab T, int nclin, int n_li, const int *li_idx, const double *Adense,
+                           const double *g, const double *J, const double *mu, double *gA)
+{
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (long long)P * T.nC) return;
+    const int p = (int)(q / T.nC), c = (int)(q - (long long)p * T.nC);
+    const int m = n_li + T.ncnln, nbps = T.nbps, S = T.S;
+    const double *mup = mu + (size_t)p * m;
+    double acc = g[q];
+    for (int i = 0; i < n_li; i++) acc += mup[i] * Adense[(size_t)c * nclin + li_idx[i]];
+    if (T.ncnln > 0) {
+        const double *Jp = J + (size_t)p * T.ncnln * S;
+        const double *mun = mup + n_li;
+        for (int j = 0; j < T.nout; j++) {
+            const int cl = c - T.iC[j];
+            if (cl < 0 || cl >= T.ncoef[j]) continue;
+            const int ord = T.order[j], s0 = T.jk0[j];
+            if (cl < ord) /* initial rows: columns from iC_j, src/colloc.c:254 */
+                for (int r = 0; r < T.nnlic; r++) acc += mun[r] * Jp[(size_t)r * S + s0 + cl];
+            if (T.nnltc > 0) {
+                const int lo = T.col_lo[c], hi = T.col_hi[c];
+                for (int bp = lo; bp <= hi; bp++) {
+                    const int k = cl - T.off[j][bp];
+                    if (k < 0 || k >= ord) continue;
+                    for (int mm = 0; mm < T.nnltc; mm++)
+                        acc += mun[T.nnlic + mm * nbps + bp] *
+                               Jp[(size_t)T.nnlic * S + ((size_t)mm * S + s0 + k) * nbps + bp];
+                }
+            }
+            if (T.nnlfc > 0) {
+                const int k = cl - T.off[j][nbps - 1];
+                const int rb = T.nnlic + T.nnltc * nbps;
+                if (k >= 0 && k < ord)
+                    for (int r = 0; r < T.nnlfc; r++) acc += mun[rb + r] * Jp[(size_t)(rb + r) * S + s0 + k];
+            }
+        }
+    }
+    gA[q] = acc;
+}
+
+/* between two rounds: multipliers <- mu, penalty up if the violation stalls, BFGS restarted;
+ * a problem is finished when it is feasible to ctol and its inner iteration had converged */
+__global__ void k_alm_outer(int P, int m, int nr, const double *mu, double *lam, double *rho, const double *viol,
+                            double *violprev, double ctol, double rho_mul, int last, double *H, int *state, int *fails,
+                            int *fin, int *count)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    if (fin[p] == 0) {
+        const bool inner_ok = state[p] != 0; /* reduced gradient below gtol (1) or no further decrease (2) */
+        if (viol[p] <= ctol && inner_ok) {
+            fin[p] = state[p];
+        } else if (!last) {
+            for (int i = 0; i < m; i++) lam[(size_t)p * m + i] = mu[(size_t)p * m + i];
+            if (viol[p] > 0.25 * violprev[p] && rho[p] < 1e8) rho[p] *= rho_mul;
+            violprev[p] = viol[p];
+            /* the merit function changed: the next BFGS update would pair gradients of two different
+             * functions, so it is skipped (-2 = no previous step, inverse Hessian kept) */
+            state[p] = 0;
+            fails[p] = -2;
+        }
+    }
+    if (fin[p] != 0) {
+        state[p] = 1; /* inert for the inner kernels */
+        atomicAdd(count, 1);
+    }
+}
+
+__global__ void k_alm_prep(int P, int m, double rho0, double *lam, double *rho, double *violprev, int *fin)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    for (int i = 0; i < m; i++) lam[(size_t)p * m + i] = 0.0;
+    rho[p] = rho0;
+    violprev[p] = 1e300;
+    fin[p] = 0;
+}
+
 int check_avs(const AV *av, int n, const ntgb_setup *s, const char *what)
 {
     if (n < 0 || (n > 0 && av == nullptr)) return fail(NTGB_EINVAL, "%s: bad active-variable list", what);
@@ -631,6 +773,9 @@ void ntgb_destroy(ntgb_problem *pb)
     if (pb->ls.Ct) cudaFree(pb->ls.Ct);
     if (pb->ls.res) cudaFree(pb->ls.res);
     if (pb->ls.lv) cudaFree(pb->ls.lv);
+    if (pb->alm.blob) cudaFree(pb->alm.blob);
+    if (pb->alm.tblob) cudaFree(pb->alm.tblob);
+    if (pb->alm.iblob) cudaFree(pb->alm.iblob);
     if (pb->red.blob) cudaFree(pb->red.blob);
     if (pb->red.iblob) cudaFree(pb->red.iblob);
     for (auto &h : pb->hs) {
@@ -1363,6 +1508,192 @@ int ntgb_solve_eq(ntgb_problem *pb, int P, double *C, double *f, int *iters, int
     }
     if (iters) CUDA_TRY(cudaMemcpyAsync(iters, its, sizeof(int) * (size_t)P, cudaMemcpyDeviceToDevice, st));
     if (status) CUDA_TRY(cudaMemcpyAsync(status, state, sizeof(int) * (size_t)P, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int ntgb_solve_nlp(ntgb_problem *pb, int P, double *C, double *f, double *viol_out, int *iters, int *status,
+                   const ntgb_nlp_opts *opts, void *stream)
+{
+    if (!pb || !C) return fail(NTGB_EINVAL, "ntgb_solve_nlp: null argument");
+    if (P <= 0) return 0;
+    const ntgb_dims &dm = pb->dims;
+    ntgb_nlp_opts o{40, 80, 1e-6, 1e-6, 10.0, 10.0, 1e-4, 4};
+    if (opts) {
+        if (opts->max_outer > 0) o.max_outer = opts->max_outer;
+        if (opts->max_inner > 0) o.max_inner = opts->max_inner;
+        if (opts->gtol > 0.0) o.gtol = opts->gtol;
+        if (opts->ctol > 0.0) o.ctol = opts->ctol;
+        if (opts->rho0 > 0.0) o.rho0 = opts->rho0;
+        if (opts->rho_mul > 1.0) o.rho_mul = opts->rho_mul;
+        if (opts->c1 > 0.0) o.c1 = opts->c1;
+        if (opts->check_every > 0) o.check_every = opts->check_every;
+    }
+    DeviceGuard dg(pb->device);
+    if (!dg.ok) return fail(NTGB_ECUDA, "cannot select device %d", pb->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nC = dm.nC, nclin = dm.nclin, ncnln = dm.ncnln;
+    int rc;
+    auto &al = pb->alm;
+    if (!al.ready) {
+        /* split the linear rows: equalities are eliminated, the rest become general constraints */
+        std::vector<int> eq, li;
+        for (int i = 0; i < nclin; i++) (pb->lin_lb[i] == pb->lin_ub[i] ? eq : li).push_back(i);
+        const int me = (int)eq.size();
+        std::vector<double> Ae((size_t)std::max(me, 1) * nC, 0.0), be((size_t)me);
+        for (int r = 0; r < me; r++) {
+            be[r] = pb->lin_lb[eq[r]];
+            for (int c = 0; c < nC; c++) Ae[r + (size_t)c * me] = pb->A[eq[r] + (size_t)c * nclin];
+        }
+        std::vector<double> N, Cpart;
+        int nr = 0;
+        if ((rc = reduce_linear(Ae, me, nC, be, N, Cpart, nr))) return rc;
+        if (nr > kSolveMaxNr)
+            return fail(NTGB_ELIMIT, "ntgb_solve_nlp: %d free directions after eliminating the linear equalities (limit %d)",
+                        nr, kSolveMaxNr);
+        al.nr = nr;
+        al.n_li = (int)li.size();
+        al.m = al.n_li + ncnln;
+        if (N.empty()) N.push_back(0.0);
+        if ((rc = dev_upload(pb, &al.N, N.data(), N.size()))) return rc;
+        if ((rc = dev_upload(pb, &al.Cpart, Cpart.data(), Cpart.size()))) return rc;
+        if (li.empty()) li.push_back(0);
+        if ((rc = dev_upload(pb, &al.li_idx, li.data(), li.size()))) return rc;
+        /* bounds of the general constraints: NPSOL's bl/bu behind the variables and, for the
+         * linear rows, the expanded linear bounds */
+        std::vector<double> bl((size_t)nC + nclin + ncnln), bu(bl.size());
+        if ((rc = ntgb_get_bounds(pb, bl.data(), bu.data()))) return rc;
+        std::vector<double> hl((size_t)std::max(al.m, 1), 0.0), hu((size_t)std::max(al.m, 1), 0.0);
+        for (int i = 0; i < al.n_li; i++) { hl[i] = pb->lin_lb[li[i]]; hu[i] = pb->lin_ub[li[i]]; }
+        for (int i = 0; i < ncnln; i++) { hl[al.n_li + i] = bl[(size_t)nC + nclin + i]; hu[al.n_li + i] = bu[(size_t)nC + nclin + i]; }
+        if ((rc = dev_upload(pb, &al.hl, hl.data(), hl.size()))) return rc;
+        if ((rc = dev_upload(pb, &al.hu, hu.data(), hu.size()))) return rc;
+        std::vector<double> Ad = pb->A;
+        if (Ad.empty()) Ad.push_back(0.0);
+        if ((rc = dev_upload(pb, &al.A, Ad.data(), Ad.size()))) return rc;
+        al.ready = true;
+    }
+    const int nr = al.nr, m = al.m, n_li = al.n_li;
+    constexpr int kNalpha = 12;
+    const size_t Pz = (size_t)P, Q = Pz * kNalpha;
+    const size_t mz = (size_t)std::max(m, 1), ncz = (size_t)std::max(ncnln, 1), nlz = (size_t)std::max(nclin, 1);
+    if (Pz > al.cap) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (al.blob) cudaFree(al.blob);
+        if (al.tblob) cudaFree(al.tblob);
+        if (al.iblob) cudaFree(al.iblob);
+        al.blob = al.tblob = nullptr; al.iblob = nullptr; al.cap = 0;
+        const size_t nd = Pz * ((size_t)4 * nr + (size_t)nr * nr + 3 * (size_t)nC + 2 * mz + ncz + ncz * dm.sorder + nlz + 10) + kNalpha;
+        const size_t nt = Q * ((size_t)nC + ncz + nlz + 4);
+        CUDA_TRY(cudaMalloc((void **)&al.blob, nd * sizeof(double)));
+        CUDA_TRY(cudaMalloc((void **)&al.tblob, nt * sizeof(double)));
+        CUDA_TRY(cudaMalloc((void **)&al.iblob, ((size_t)4 * P + 1) * sizeof(int)));
+        al.cap = Pz;
+    }
+    const size_t cap = al.cap;
+    double *q = al.blob;
+    double *y = q;      q += cap * nr;
+    double *yp = q;     q += cap * nr;
+    double *grp = q;    q += cap * nr;
+    double *d = q;      q += cap * nr;
+    double *H = q;      q += cap * nr * nr;
+    double *dC = q;     q += cap * nC;
+    double *g = q;      q += cap * nC;
+    double *gA = q;     q += cap * nC;
+    double *lam = q;    q += cap * mz;
+    double *mu = q;     q += cap * mz;
+    double *cc = q;     q += cap * ncz;
+    double *J = q;      q += cap * ncz * dm.sorder;
+    double *lin = q;    q += cap * nlz;
+    double *fv = q;     q += cap;
+    double *LA = q;     q += cap;
+    double *viol = q;   q += cap;
+    double *violp = q;  q += cap;
+    double *rho = q;    q += cap;
+    double *phi0 = q;   q += cap;
+    double *dphi0 = q;  q += cap;
+    double *ab = q;     q += cap;
+    double *pbest = q;  q += cap;
+    double *alphas = q;
+    const size_t capq = cap * kNalpha;
+    double *t = al.tblob;
+    double *Ct = t;     t += capq * nC;
+    double *ct = t;     t += capq * ncz;
+    double *lint = t;   t += capq * nlz;
+    double *ft = t;     t += capq;
+    double *res = t;    /* [Q][2] */
+    int *state = al.iblob, *its = state + cap, *fails = its + cap, *fin = fails + cap, *count = fin + cap;
+
+    double ha[kNalpha];
+    for (int a = 0; a < kNalpha; a++) ha[a] = std::ldexp(1.0, -a);
+    CUDA_TRY(cudaMemcpyAsync(alphas, ha, sizeof ha, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(res, 0, sizeof(double) * 2 * Q, st));
+    const unsigned grid = (unsigned)((P + 127) / 128);
+    CUDA_TRY(launch(k_solve_init, grid, 128, st, P, nC, nr, al.N, al.Cpart, C, y, H, state, its, fails));
+    CUDA_TRY(launch(k_alm_prep, grid, 128, st, P, m, o.rho0, lam, rho, violp, fin));
+    CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(int), st));
+
+    ntgb_eval_args ea;
+    memset(&ea, 0, sizeof ea);
+    ea.P = P; ea.C = C; ea.mode_obj = 2; ea.mode_con = ncnln > 0 ? 2 : -1; ea.f = fv; ea.g = g; ea.c = cc; ea.J = J;
+    ea.jac_layout = ncnln > 0 ? NTGB_JAC_BAND : NTGB_JAC_NONE; ea.stream = st;
+    ntgb_eval_args et;
+    memset(&et, 0, sizeof et);
+    et.P = (int)Q; et.C = Ct; et.mode_obj = 0; et.mode_con = ncnln > 0 ? 0 : -1; et.f = ft; et.c = ct;
+    et.jac_layout = NTGB_JAC_NONE; et.stream = st;
+    if (Q > 0x7fffffffull) return fail(NTGB_EINVAL, "P*nalpha too large");
+
+    auto assemble = [&]() -> int { /* f, g, c, J, lin at C -> mu, L_A, violation, grad L_A */
+        int r2;
+        if ((r2 = ntgb_eval(pb, &ea))) return r2;
+        if (n_li > 0 && (r2 = ntgb_eval_linear(pb, P, C, lin, nullptr, st))) return r2;
+        const unsigned gw = (unsigned)(((long long)P * 32 + 127) / 128);
+        CUDA_TRY(launch(k_alm_mu, gw, 128, st, P, 1, ncnln, nclin, n_li, al.li_idx, al.hl, al.hu, lam, rho, fv, cc, lin, mu,
+                        LA, viol, 1));
+        const long long tot = (long long)P * nC;
+        CUDA_TRY(launch(k_alm_grad, (unsigned)((tot + 127) / 128), 128, st, P, pb->tab, nclin, n_li, al.li_idx, al.A, g, J,
+                        mu, gA));
+        return 0;
+    };
+
+    for (int outer = 0; outer < o.max_outer; outer++) {
+        for (int it = 0; it < o.max_inner; it++) {
+            if ((rc = assemble())) return rc;
+            CUDA_TRY(launch(k_solve_dir, grid, 128, st, P, nC, nr, al.N, LA, gA, o.gtol, y, yp, grp, H, d, dC, phi0, dphi0,
+                            state, fails, count));
+            if ((it + 1) % o.check_every == 0) {
+                int done = 0;
+                CUDA_TRY(cudaMemcpyAsync(&done, count, sizeof(int), cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+                if (done >= P) break;
+            }
+            /* Armijo line search on the augmented Lagrangian: P*12 trial points in one evaluation */
+            const long long totc = (long long)Q * nC;
+            CUDA_TRY(launch(k_ls_trial, (unsigned)((totc + 255) / 256), 256, st, C, dC, alphas, P, kNalpha, nC, Ct));
+            if ((rc = ntgb_eval(pb, &et))) return rc;
+            if (n_li > 0 && (rc = ntgb_eval_linear(pb, (int)Q, Ct, lint, nullptr, st))) return rc;
+            const unsigned gq = (unsigned)(((long long)Q * 32 + 127) / 128);
+            CUDA_TRY(launch(k_alm_mu, gq, 128, st, (int)Q, kNalpha, ncnln, nclin, n_li, al.li_idx, al.hl, al.hu, lam, rho, ft,
+                            ct, lint, (double *)nullptr, res, (double *)nullptr, 2));
+            CUDA_TRY(launch(k_ls_pick, grid, 128, st, res, (const double *)nullptr, alphas, P, kNalpha, 0.0, o.c1, phi0, dphi0,
+                            C, dC, nC, ab, pbest, (double *)nullptr));
+            CUDA_TRY(launch(k_solve_update, grid, 128, st, P, nC, nr, al.N, al.Cpart, phi0, ab, pbest, d, y, H, C, state, its,
+                            fails, count));
+        }
+        /* round finished: fresh multipliers at the point reached, then the outer update */
+        if ((rc = assemble())) return rc;
+        CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(int), st));
+        CUDA_TRY(launch(k_alm_outer, grid, 128, st, P, m, nr, mu, lam, rho, viol, violp, o.ctol, o.rho_mul,
+                        outer + 1 == o.max_outer ? 1 : 0, H, state, fails, fin, count));
+        int done = 0;
+        CUDA_TRY(cudaMemcpyAsync(&done, count, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (done >= P) break;
+    }
+    if (f) CUDA_TRY(cudaMemcpyAsync(f, fv, sizeof(double) * Pz, cudaMemcpyDeviceToDevice, st));
+    if (viol_out) CUDA_TRY(cudaMemcpyAsync(viol_out, viol, sizeof(double) * Pz, cudaMemcpyDeviceToDevice, st));
+    if (iters) CUDA_TRY(cudaMemcpyAsync(iters, its, sizeof(int) * Pz, cudaMemcpyDeviceToDevice, st));
+    if (status) CUDA_TRY(cudaMemcpyAsync(status, fin, sizeof(int) * Pz, cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return 0;
 }

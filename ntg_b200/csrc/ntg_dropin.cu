@@ -282,11 +282,13 @@ void ntg(int nout, double *bps, int nbps, int *kninterv, double **knots, int *or
 
     npsol_t npsol = (npsol_t)dlsym(RTLD_DEFAULT, "npsol_");
     if (!npsol) {
-        /* No NPSOL in the process.  Problems of the shipped examples' class (no nonlinear
-         * constraints, linear equalities only) are solved by the library's own reduced-space BFGS
-         * (ntgb_solve_eq) instead; everything else cannot be solved here. */
-        bool builtin = NPncnln == 0 && getenv("NTG_B200_NO_BUILTIN_SOLVER") == nullptr;
-        for (int i = 0; builtin && i < NPnclin; i++) builtin = bl[NPn + i] == bu[NPn + i];
+        /* No NPSOL in the process: the library's own batched solvers stand in (P = 1).  Problems
+         * of the shipped examples' class (no nonlinear constraints, linear equalities only) go to the
+         * reduced-space BFGS (ntgb_solve_eq), everything else to the augmented-Lagrangian driver
+         * (ntgb_solve_nlp).  NTG_B200_NO_BUILTIN_SOLVER=1 switches this off. */
+        const bool builtin = getenv("NTG_B200_NO_BUILTIN_SOLVER") == nullptr;
+        bool eq_only = NPncnln == 0;
+        for (int i = 0; eq_only && i < NPnclin; i++) eq_only = bl[NPn + i] == bu[NPn + i];
         int rc = NTGB_EINVAL;
         if (builtin) {
             double *dC = nullptr;
@@ -294,21 +296,25 @@ void ntg(int nout, double *bps, int nbps, int *kninterv, double **knots, int *or
             int st = 0;
             double fv = 0.0;
             cudaSetDevice(device);
-            if (cudaMalloc((void **)&dC, sizeof(double) * ((size_t)NPn + 1)) == cudaSuccess &&
+            if (cudaMalloc((void **)&dC, sizeof(double) * ((size_t)NPn + 2)) == cudaSuccess &&
                 cudaMalloc((void **)&dst, sizeof(int) * 2) == cudaSuccess &&
                 cudaMemcpy(dC, initialguess, sizeof(double) * NPn, cudaMemcpyHostToDevice) == cudaSuccess) {
-                rc = ntgb_solve_eq(pb, 1, dC, dC + NPn, dst, dst + 1, nullptr, nullptr);
+                /* equalities only: reduced-space BFGS; anything else: augmented Lagrangian on top of it */
+                rc = eq_only ? ntgb_solve_eq(pb, 1, dC, dC + NPn, dst, dst + 1, nullptr, nullptr)
+                             : ntgb_solve_nlp(pb, 1, dC, dC + NPn, dC + NPn + 1, dst, dst + 1, nullptr, nullptr);
                 if (rc == 0 && cudaMemcpy(&st, dst + 1, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess &&
                     cudaMemcpy(&fv, dC + NPn, sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess &&
                     cudaMemcpy(initialguess, dC, sizeof(double) * NPn, cudaMemcpyDeviceToHost) == cudaSuccess) {
                     if (objective) *objective = fv;
-                    /* NPSOL's codes: 0 optimal, 1 no further improvement possible, 4 iteration limit */
-                    if (inform) *inform = st == 1 ? 0 : (st == 2 ? 1 : 4);
+                    /* NPSOL's codes: 0 optimal, 1 no further improvement possible, 4 iteration limit
+                     * (solve_nlp: 6 = not converged, the nonlinear constraints may be violated) */
+                    if (inform) *inform = st == 1 ? 0 : (st == 2 ? 1 : (eq_only ? 4 : 6));
                     fprintf(stderr,
                             "ntg: NPSOL (npsol_) is not linked into this process; solved with ntg_b200's built-in\n"
-                            "     reduced-space BFGS instead (n=%d, nclin=%d equalities, no nonlinear constraints).\n"
+                            "     %s instead (n=%d, nclin=%d, ncnln=%d).\n"
                             "     istate, clambda and R are not set on this path.\n",
-                            NPn, NPnclin);
+                            eq_only ? "reduced-space BFGS" : "augmented-Lagrangian / reduced-space BFGS", NPn, NPnclin,
+                            NPncnln);
                 } else if (rc == 0) {
                     rc = NTGB_ECUDA;
                 }

@@ -13,7 +13,7 @@ from typing import Dict, Optional
 import numpy as np
 
 from . import abi
-from .abi import (JAC_BAND, JAC_DENSE, JAC_NONE, BuiltSetup, NtgbDims, NtgbEvalArgs, NtgbPack, SolveOpts,
+from .abi import (JAC_BAND, JAC_DENSE, JAC_NONE, BuiltSetup, NtgbDims, NtgbEvalArgs, NtgbPack, SolveOpts, NlpOpts,
                   ProblemSpec, c_double_p, c_int_p)
 
 _LIBDIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
@@ -51,6 +51,9 @@ def core() -> C.CDLL:
         lib.ntgb_solve_eq.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p]
         lib.ntgb_solve_eq.restype = C.c_int
+        lib.ntgb_solve_nlp.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.ntgb_solve_nlp.restype = C.c_int
         lib.ntgb_linesearch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                         C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]
@@ -291,6 +294,23 @@ class Problem:
         _check(core().ntgb_solve_eq(self._h, P, Cdev.data_ptr(), f.data_ptr(), it.data_ptr(), stt.data_ptr(),
                                     C.addressof(opts), st))
         return f, it, stt
+
+    def solve_nlp(self, Cdev, max_outer=0, max_inner=0, gtol=0.0, ctol=0.0, rho0=0.0, rho_mul=0.0, c1=0.0,
+                  check_every=0):
+        """batched augmented-Lagrangian solve (ntgb_solve_nlp); Cdev [P][nC] is overwritten.
+        Returns f [P], violation [P], iters [P], status [P]."""
+        import torch
+        P = Cdev.shape[0]
+        f = torch.zeros(P, dtype=torch.float64, device=Cdev.device)
+        v = torch.zeros(P, dtype=torch.float64, device=Cdev.device)
+        it = torch.zeros(P, dtype=torch.int32, device=Cdev.device)
+        stt = torch.zeros(P, dtype=torch.int32, device=Cdev.device)
+        opts = NlpOpts(int(max_outer), int(max_inner), float(gtol), float(ctol), float(rho0), float(rho_mul),
+                       float(c1), int(check_every))
+        st = torch.cuda.current_stream(Cdev.device).cuda_stream
+        _check(core().ntgb_solve_nlp(self._h, P, Cdev.data_ptr(), f.data_ptr(), v.data_ptr(), it.data_ptr(),
+                                     stt.data_ptr(), C.addressof(opts), st))
+        return f, v, it, stt
 
     def spline_interp(self, Cdev, tdev):
         import torch

@@ -182,13 +182,31 @@ def _run_ntg_no_npsol(constraints, env=None):
 
 
 def test_ntg_without_npsol_reports_it():
-    """NPSOL absent and a problem with nonlinear constraints (or the built-in solver switched off)
-    -> ntg() sets up on the GPU, says so, sets inform, solves nothing."""
+    """NPSOL absent and the built-in solvers switched off -> ntg() sets up on the GPU, says so,
+    sets inform, solves nothing."""
+    for constraints in (True, False):
+        out, err = _run_ntg_no_npsol(constraints, {"NTG_B200_NO_BUILTIN_SOLVER": "1"})
+        assert "INFORM -1000" in out, out + err
+        assert "NPSOL" in err
+
+
+def test_ntg_without_npsol_solves_constrained_problems(port):
+    """NPSOL absent, van der Pol with the nonlinear input constraint |u| <= 2 (pack VDP-C): ntg()
+    falls back to the augmented-Lagrangian solver and returns a feasible point that is at least as
+    good as the start."""
     out, err = _run_ntg_no_npsol(True)
-    assert "INFORM -1000" in out, out + err
-    assert "NPSOL" in err
-    out, err = _run_ntg_no_npsol(False, {"NTG_B200_NO_BUILTIN_SOLVER": "1"})
-    assert "INFORM -1000" in out, out + err
+    lines = dict(l.split(" ", 1) for l in out.strip().splitlines() if " " in l)
+    assert int(lines["INFORM"]) in (0, 1), out + err
+    assert "augmented-Lagrangian" in err
+    x = np.array([float(v) for v in lines["X"].split()])
+    spec = configs.vanderpol(20, constraints=True)
+    o = port.eval(spec, x[None, :], mode_obj=2, mode_con=2, dense=False, band=False, linear=True)
+    nC = spec.nC
+    A, b = o["A"], o["bl"][nC:nC + spec.nclin]
+    assert np.abs(A @ x - b).max() < 1e-9
+    lb, ub = o["bl"][nC + spec.nclin:], o["bu"][nC + spec.nclin:]
+    assert (o["c"][0] >= lb - 2e-6).all() and (o["c"][0] <= ub + 2e-6).all()
+    assert abs(float(lines["OBJ"]) - o["f"][0]) <= 1e-12 * abs(o["f"][0])
 
 
 def test_ntg_without_npsol_solves_equality_problems(port):
@@ -348,4 +366,68 @@ def test_solve_refuses_inequalities_and_nonlinear():
     pb = Problem(spec, 0)
     with pytest.raises(NtgError):
         pb.solve_eq(torch.zeros((4, spec.nC), dtype=torch.float64, device="cuda"))
+    pb.close()
+
+
+def _kincar_active_constraints(nbps=40, ninterv=4):
+    """lane change with enough freedom (nC = 22, 10 free directions) and nonlinear bounds that are
+    ACTIVE at the solution: speed^2 <= 66.2 (66.5 unconstrained), |curvature numerator| <= 7.2 (7.66)"""
+    import dataclasses
+    base = configs.kincar(nbps, constraints=True, name="nlp_kincar")
+    kw = {f.name: getattr(base, f.name) for f in dataclasses.fields(base)}
+    kw.update(ninterv=[ninterv, ninterv], knots=None, bps=None)
+    spec = type(base)(**kw)
+    lo, up = spec.lowerb.copy(), spec.upperb.copy()
+    lo[-2], up[-2] = 0.0, 66.2
+    lo[-1], up[-1] = -7.2, 7.2
+    spec.lowerb, spec.upperb = lo, up
+    return spec
+
+
+def test_batched_nlp_solver_vs_slsqp(port):
+    """ntgb_solve_nlp (augmented Lagrangian + reduced-space BFGS, every step a batched kernel) on 512
+    lane-change problems with active nonlinear constraints, from random starts: feasibility and the
+    linear equalities checked with the ORACLE, the cost against scipy SLSQP (started next to the
+    GPU's answer so that it converges -- from the random starts it fails on most of them)."""
+    import torch
+    from scipy.optimize import minimize
+    from ntg_b200 import Problem
+    spec = _kincar_active_constraints()
+    nC = spec.nC
+    P = 512
+    X = configs.coefficients("cfg3", P, spec, seed=5)
+    pb = Problem(spec, 0)
+    Cd = torch.from_numpy(X).cuda()
+    f, v, it, st = pb.solve_nlp(Cd)
+    Cs, f, v, st = Cd.cpu().numpy(), f.cpu().numpy(), v.cpu().numpy(), st.cpu().numpy()
+    ok = st >= 1
+    assert ok.mean() >= 0.9, f"only {ok.mean():.2f} of the problems converged"
+    o = port.eval(spec, Cs, mode_obj=0, mode_con=0, dense=False, band=False, linear=True)
+    A, bl, bu = o["A"], o["bl"], o["bu"]
+    b = bl[nC:nC + spec.nclin]
+    assert np.abs(Cs @ A.T - b).max() <= 1e-8 * (1 + np.abs(b).max()), "linear equalities"
+    lb, ub = bl[nC + spec.nclin:], bu[nC + spec.nclin:]
+    viol = np.maximum(np.maximum(lb - o["c"], o["c"] - ub), 0).max(axis=1)
+    assert (viol[ok] <= 1e-4).all(), viol[ok].max()
+    assert_close(f, o["f"], "reported cost equals the oracle's at the returned point")
+    assert (o["c"][ok].max(axis=1) > 7.19).all(), "the curvature bound is active at the solution"
+
+    def fun(c):
+        e = port.eval(spec, c[None, :], mode_obj=2, mode_con=-1, dense=False, band=False)
+        return float(e["f"][0]), e["g"][0]
+
+    def con(c):
+        e = port.eval(spec, c[None, :], mode_obj=-1, mode_con=2, dense=True, band=False)
+        Jd = np.nan_to_num(e["Jdense"][0], nan=0.0)
+        return e["c"][0], (Jd.T if Jd.shape[0] == nC else Jd)
+
+    cons = [{"type": "eq", "fun": lambda c: A @ c - b, "jac": lambda c: A},
+            {"type": "ineq", "fun": lambda c: con(c)[0] - lb, "jac": lambda c: con(c)[1]},
+            {"type": "ineq", "fun": lambda c: ub - con(c)[0], "jac": lambda c: -con(c)[1]}]
+    idx = np.flatnonzero(ok)[:3]
+    for p in idx:
+        r = minimize(fun, Cs[p] + 1e-3, jac=True, method="SLSQP", constraints=cons, options={"ftol": 1e-13, "maxiter": 300})
+        assert r.success, r.message
+        assert abs(r.fun - f[p]) <= 2e-5 * abs(r.fun), (r.fun, f[p])
+        assert np.abs(r.x - Cs[p]).max() <= 1e-2
     pb.close()

@@ -431,3 +431,59 @@ def test_batched_nlp_solver_vs_slsqp(port):
         assert abs(r.fun - f[p]) <= 2e-5 * abs(r.fun), (r.fun, f[p])
         assert np.abs(r.x - Cs[p]).max() <= 1e-2
     pb.close()
+
+
+_EXAMPLE_MAIN_CODE = r"""
+import ctypes as C, os, sys
+sys.path.insert(0, %r)
+from ntg_b200 import problem
+lib = problem.load_pack("ref_%s")
+os.chdir(%r)
+main = getattr(lib, "ntg_example_%s_main")
+main.restype = C.c_int
+if %r == "kincar":
+    argv = (C.c_char_p * 2)(b"kincar", None)
+    rc = main(1, argv)
+else:
+    rc = main()
+sys.stdout.flush()
+print("MAIN_RC", rc)
+"""
+
+
+@pytest.mark.parametrize("example", ["vanderpol", "kincar"])
+def test_reference_examples_end_to_end_without_npsol(port, example, tmp_path):
+    """examples/vanderpol.c and examples/kincar.c, UNMODIFIED, as whole programs with NO NPSOL in
+    the process: main() calls ntg(), ntg() solves with the built-in reduced-space BFGS, the program
+    prints / stores its result as it would after NPSOL (examples/vanderpol.c:192 writes ./coef1,
+    examples/kincar.c:393-406 prints the interpolated trajectory)."""
+    import subprocess
+    import sys
+    from ntg_b200 import build
+    if not os.path.exists(build.pack_so(f"ref_{example}")):
+        pytest.skip("drop-in example packs are built where /root/reference exists")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = _EXAMPLE_MAIN_CODE % (root, example, str(tmp_path), example, example)
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert "MAIN_RC 0" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "built-in" in p.stderr and "reduced-space BFGS" in p.stderr
+    if example == "vanderpol":
+        coef = np.array(open(tmp_path / "coef1").read().split(), dtype=np.float64)
+        spec = configs.vanderpol(20, constraints=False)
+        assert coef.shape == (spec.nC,)
+        o = port.eval(spec, coef[None, :], mode_obj=2, mode_con=-1, dense=False, band=False, linear=True)
+        nC = spec.nC
+        A, b = o["A"], o["bl"][nC:nC + spec.nclin]
+        assert np.abs(A @ coef - b).max() < 1e-4          # %g keeps 6 significant digits
+        N = _null_basis(A)
+        assert np.abs(o["g"][0] @ N).max() < 1e-3, "coef1 is a stationary point of the problem the example poses"
+        f1 = port.eval(spec, np.ones((1, nC)), mode_obj=0, mode_con=-1, dense=False, band=False)["f"][0]
+        assert o["f"][0] < f1                              # better than the example's initial guess of ones
+    else:
+        rows = [l.split() for l in p.stdout.splitlines() if len(l.split()) == 6]
+        T = np.array(rows[-30:], dtype=np.float64)         # time x y theta v delta
+        assert T.shape == (30, 6)
+        np.testing.assert_allclose(T[0, :3], [0.0, 0.0, -2.0], atol=1e-3)
+        np.testing.assert_allclose(T[-1, :3], [5.0, 40.0, 2.0], atol=1e-3)
+        np.testing.assert_allclose(T[[0, -1], 4], [8.0, 8.0], rtol=1e-3)   # speed at both ends
+        assert (np.diff(T[:, 1]) > 0).all() and (np.diff(T[:, 2]) >= -1e-6).all()   # a lane change

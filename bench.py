@@ -390,6 +390,54 @@ def time_e2e(torch, pb, spec, cfg, P, steps, warmup, full: bool):
                      "(objective, violation) table to host; g, c, J computed and left resident in HBM")}
 
 
+def time_solvers(torch, device, fast):
+    """Wall time of the two batched solvers on the lane-change problem of examples/kincar.c:
+    ntgb_solve_eq (linear equalities only, as shipped) and ntgb_solve_nlp (active speed and
+    curvature bounds).  Host wall clock around the synchronous C call, after one warm-up solve."""
+    import dataclasses
+    from ntg_b200 import Problem
+    out = {}
+    s1 = configs.kincar(64, constraints=False, name="solve_kincar_64bps")
+    P1 = 65536
+    X1 = torch.from_numpy(configs.coefficients("cfg3", P1, s1, seed=3)).to(f"cuda:{device}")
+    pb = Problem(s1, device, fast=fast)
+    pb.solve_eq(X1.clone(), max_iter=100)
+    C1 = X1.clone()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    _, it, st = pb.solve_eq(C1, max_iter=100)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out["solve_eq"] = {"workload": "kincar lane change, 64 breakpoints, linear equalities only", "problems": P1,
+                       "ms": dt * 1e3, "problems_per_s": P1 / dt, "iterations_mean": float(it.float().mean()),
+                       "converged_frac": float((st >= 1).float().mean())}
+    pb.close()
+    base = configs.kincar(40, constraints=True, name="solve_kincar_active")
+    kw = {f.name: getattr(base, f.name) for f in dataclasses.fields(base)}
+    kw.update(ninterv=[4, 4], knots=None, bps=None)
+    s2 = type(base)(**kw)
+    lo, up = s2.lowerb.copy(), s2.upperb.copy()
+    lo[-2], up[-2], lo[-1], up[-1] = 0.0, 66.2, -7.2, 7.2
+    s2.lowerb, s2.upperb = lo, up
+    P2 = 16384
+    X2 = torch.from_numpy(configs.coefficients("cfg3", P2, s2, seed=5)).to(f"cuda:{device}")
+    pb = Problem(s2, device, fast=fast)
+    pb.solve_nlp(X2[:256].clone())
+    C2 = X2.clone()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    _, v, it, st = pb.solve_nlp(C2)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out["solve_nlp"] = {"workload": "kincar lane change, 40 breakpoints, 4 intervals, active speed^2 / curvature bounds",
+                        "problems": P2, "ms": dt * 1e3, "problems_per_s": P2 / dt,
+                        "iterations_mean": float(it.float().mean()), "converged_frac": float((st >= 1).float().mean()),
+                        "violation_max": float(v.max())}
+    pb.close()
+    torch.cuda.empty_cache()
+    return out
+
+
 _REAL_STDOUT = None
 
 
@@ -486,6 +534,10 @@ def main():
                            "l2": f"ring of {r2['nset']} buffer sets, {r2['footprint_mb']:.0f} MB"}
             pb2.close()
             torch.cuda.empty_cache()
+        try:   # the batched solvers built on the evaluator (informative, not the metric)
+            others["solvers"] = time_solvers(torch, local, fast)
+        except Exception as e:  # never let an extra take the bench line down
+            others["solvers"] = {"error": str(e)[:200]}
 
     if rank == 0:
         bytes_launch = P * spec.bytes_per_eval()

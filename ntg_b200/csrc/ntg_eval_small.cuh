@@ -186,6 +186,20 @@ __device__ __forceinline__ void trap_run_fast(const double *row, const double *W
         g[0] = g[0] + Wf[n] * row[n];
         n++;
     }
+    for (; n + 7 <= n1; n += 8) { /* eight loads in flight, two multiply-adds per partial sum */
+        const double2 d01 = *reinterpret_cast<const double2 *>(row + n), d23 = *reinterpret_cast<const double2 *>(row + n + 2);
+        const double2 d45 = *reinterpret_cast<const double2 *>(row + n + 4), d67 = *reinterpret_cast<const double2 *>(row + n + 6);
+        const double2 w01 = *reinterpret_cast<const double2 *>(Wf + n), w23 = *reinterpret_cast<const double2 *>(Wf + n + 2);
+        const double2 w45 = *reinterpret_cast<const double2 *>(Wf + n + 4), w67 = *reinterpret_cast<const double2 *>(Wf + n + 6);
+        g[0] = g[0] + w01.x * d01.x;
+        g[1] = g[1] + w01.y * d01.y;
+        g[2] = g[2] + w23.x * d23.x;
+        g[3] = g[3] + w23.y * d23.y;
+        g[0] = g[0] + w45.x * d45.x;
+        g[1] = g[1] + w45.y * d45.y;
+        g[2] = g[2] + w67.x * d67.x;
+        g[3] = g[3] + w67.y * d67.y;
+    }
     for (; n + 3 <= n1; n += 4) {
         const double2 d01 = *reinterpret_cast<const double2 *>(row + n), d23 = *reinterpret_cast<const double2 *>(row + n + 2);
         const double2 w01 = *reinterpret_cast<const double2 *>(Wf + n), w23 = *reinterpret_cast<const double2 *>(Wf + n + 2);
@@ -706,11 +720,14 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                 }
             }
         }
-        /* maximum constraint violation per problem: eight lanes per problem, then three shuffles */
+        /* maximum constraint violation per problem: eight lanes per problem, then three shuffles.
+         * Handed out from the END of the block: with fewer chains than threads these are warps that
+         * have no chain to walk, so the two passes run side by side. */
         if (con_v && A.result != nullptr) {
             const int nv = GR * 8;
+            const int tv = (int)blockDim.x - 1 - (int)threadIdx.x;
             for (int base = 0; base < nv; base += blockDim.x) {
-                const int q = base + threadIdx.x;
+                const int q = base + tv;
                 const int plr = q >> 3, part = q & 7;
                 double vm = 0.0, vn = 0.0;
                 if (q < nv) {

@@ -159,16 +159,33 @@ __device__ __forceinline__ void trap_run_exact(const double *row, const double *
         prev = d;
         n++;
     }
-    for (; n + 3 <= n1; n += 4) {
-        const double2 d01 = *reinterpret_cast<const double2 *>(row + n), d23 = *reinterpret_cast<const double2 *>(row + n + 2);
-        const double2 w01 = *reinterpret_cast<const double2 *>(wt + n), w23 = *reinterpret_cast<const double2 *>(wt + n + 2);
-        const double t0 = w01.x * (d01.x + prev), t1 = w01.y * (d01.y + d01.x), t2 = w23.x * (d23.x + d01.y),
-                     t3 = w23.y * (d23.y + d23.x);
+    if (n + 3 <= n1) {
+        /* software pipeline: the next block's loads and products are issued before this block's four
+         * dependent additions */
+        double2 d01 = *reinterpret_cast<const double2 *>(row + n), d23 = *reinterpret_cast<const double2 *>(row + n + 2);
+        double2 w01 = *reinterpret_cast<const double2 *>(wt + n), w23 = *reinterpret_cast<const double2 *>(wt + n + 2);
+        double t0 = w01.x * (d01.x + prev), t1 = w01.y * (d01.y + d01.x), t2 = w23.x * (d23.x + d01.y),
+               t3 = w23.y * (d23.y + d23.x);
+        prev = d23.y;
+        n += 4;
+        for (; n + 3 <= n1; n += 4) {
+            d01 = *reinterpret_cast<const double2 *>(row + n);
+            d23 = *reinterpret_cast<const double2 *>(row + n + 2);
+            w01 = *reinterpret_cast<const double2 *>(wt + n);
+            w23 = *reinterpret_cast<const double2 *>(wt + n + 2);
+            const double u0 = w01.x * (d01.x + prev), u1 = w01.y * (d01.y + d01.x), u2 = w23.x * (d23.x + d01.y),
+                         u3 = w23.y * (d23.y + d23.x);
+            prev = d23.y;
+            g = g + t0;
+            g = g + t1;
+            g = g + t2;
+            g = g + t3;
+            t0 = u0; t1 = u1; t2 = u2; t3 = u3;
+        }
         g = g + t0;
         g = g + t1;
         g = g + t2;
         g = g + t3;
-        prev = d23.y;
     }
     for (; n <= n1; n++) {
         const double d = row[n];
@@ -724,25 +741,29 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
          * Handed out from the END of the block: with fewer chains than threads these are warps that
          * have no chain to walk, so the two passes run side by side. */
         if (con_v && A.result != nullptr) {
-            const int nv = GR * 8;
+            /* 8 lanes per problem when they fit beside the chains, else 4 (never fewer: the loop
+             * below covers any size) */
+            const int chain_threads = (nC + 1) * GR;
+            const int LV = (chain_threads + GR * 8 <= (int)blockDim.x) ? 8 : 4;
+            const int nv = GR * LV;
             const int tv = (int)blockDim.x - 1 - (int)threadIdx.x;
             for (int base = 0; base < nv; base += blockDim.x) {
                 const int q = base + tv;
-                const int plr = q >> 3, part = q & 7;
+                const int plr = q / LV, part = q - plr * LV;
                 double vm = 0.0, vn = 0.0;
                 if (q < nv) {
                     const double *vp = viol_s + (size_t)plr * pitch;
                     int i = part;
-                    for (; i + 8 < nbps; i += 16) {
+                    for (; i + LV < nbps; i += 2 * LV) {
                         vm = fmax(vm, vp[i]);
-                        vn = fmax(vn, vp[i + 8]);
+                        vn = fmax(vn, vp[i + LV]);
                     }
                     if (i < nbps) vm = fmax(vm, vp[i]);
                 }
                 vm = fmax(vm, vn);
                 vm = fmax(vm, __shfl_xor_sync(0xffffffffu, vm, 1));
                 vm = fmax(vm, __shfl_xor_sync(0xffffffffu, vm, 2));
-                vm = fmax(vm, __shfl_xor_sync(0xffffffffu, vm, 4));
+                if (LV == 8) vm = fmax(vm, __shfl_xor_sync(0xffffffffu, vm, 4));
                 if (q < nv && part == 0 && p0 + plr < P) A.result[2 * (size_t)(p0 + plr) + 1] = vm;
             }
         }

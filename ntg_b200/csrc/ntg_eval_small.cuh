@@ -808,7 +808,8 @@ int launch_eval_small(const ntgb_launch *L)
     if (const char *er = getenv("NTG_B200_ROUNDS")) R = atoi(er); /* tuning experiments */
     if (R < 1) R = 1;
     if (R > 8) R = 8;
-    while (R > 1 && SmallSmem{G * R, nbps, T.S, T.nout, T.nC, segtot}.bytes() > 100 * 1024) R--;
+    const size_t smem_cap = (size_t)(getenv("NTG_B200_SMEMCAP") ? atoi(getenv("NTG_B200_SMEMCAP")) : 100) * 1024;
+    while (R > 1 && SmallSmem{G * R, nbps, T.S, T.nout, T.nC, segtot}.bytes() > smem_cap) R--;
     SmallSmem lay{G * R, nbps, T.S, T.nout, T.nC, segtot};
     const size_t smem = lay.bytes();
     if (smem > (size_t)L->max_smem_optin) return -1001;

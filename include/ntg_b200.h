@@ -242,7 +242,7 @@ int  ntgb_solve_eq(ntgb_problem *pb, int P, double *C, double *f, int *iters, in
  * bounds) that is minimised per problem by the same reduced-space BFGS, multipliers and penalty
  * updated between rounds.  Every step is a batched kernel: evaluation with the band Jacobian,
  * multiplier / merit kernel, J^T*mu gather per gradient column, BFGS direction, batched Armijo line
- * search on the augmented Lagrangian.  C [P][nC] (device): guesses in, solutions out.  f, viol
+ * search (16 halvings, all trial points in one evaluation) on the augmented Lagrangian.  C [P][nC] (device): guesses in, solutions out.  f, viol
  * (maximum violation of any constraint), iters (evaluations of the inner loop), status
  * (1 = violation <= ctol and reduced gradient <= gtol, 2 = violation <= ctol and no further
  * decrease of the merit function possible, 0 = not converged) are optional device outputs.
@@ -256,6 +256,7 @@ typedef struct ntgb_nlp_opts {
     double ctol;      /* constraint violation, relative to max(1, |bound|); default 1e-6 */
     double rho0;      /* initial penalty, default 10 */
     double rho_mul;   /* penalty growth when the violation does not drop by 4x, default 10 */
+    double rho_max;   /* penalty cap, default 1e4 (larger values make the inner problems ill-conditioned) */
     double c1;        /* Armijo constant, default 1e-4 */
     int check_every;  /* host reads the done counter every this many inner iterations, default 4 */
 } ntgb_nlp_opts;

@@ -85,7 +85,8 @@ class SolveOpts(C.Structure):
 class NlpOpts(C.Structure):
     """ntgb_nlp_opts (include/ntg_b200.h)"""
     _fields_ = [("max_outer", C.c_int), ("max_inner", C.c_int), ("gtol", C.c_double), ("ctol", C.c_double),
-                ("rho0", C.c_double), ("rho_mul", C.c_double), ("c1", C.c_double), ("check_every", C.c_int)]
+                ("rho0", C.c_double), ("rho_mul", C.c_double), ("rho_max", C.c_double), ("c1", C.c_double),
+                ("check_every", C.c_int)]
 
 
 class NtgbPack(C.Structure):

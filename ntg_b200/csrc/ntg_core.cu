@@ -639,7 +639,7 @@ __global__ void k_alm_grad(int P, ntgb_devtab T, int nclin, int n_li, const int 
 /* between two rounds: multipliers <- mu, penalty up if the violation stalls, BFGS restarted;
  * a problem is finished when it is feasible to ctol and its inner iteration had converged */
 __global__ void k_alm_outer(int P, int m, int nr, const double *mu, double *lam, double *rho, const double *viol,
-                            double *violprev, double ctol, double rho_mul, int last, double *H, int *state, int *fails,
+                            double *violprev, double ctol, double rho_mul, double rho_max, int last, double *H, int *state, int *fails,
                             int *fin, int *count)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -650,7 +650,7 @@ __global__ void k_alm_outer(int P, int m, int nr, const double *mu, double *lam,
             fin[p] = state[p];
         } else if (!last) {
             for (int i = 0; i < m; i++) lam[(size_t)p * m + i] = mu[(size_t)p * m + i];
-            if (viol[p] > 0.25 * violprev[p] && rho[p] < 1e8) rho[p] *= rho_mul;
+            if (viol[p] > 0.25 * violprev[p] && rho[p] * rho_mul <= rho_max) rho[p] *= rho_mul;
             violprev[p] = viol[p];
             /* the merit function changed: the next BFGS update would pair gradients of two different
              * functions, so it is skipped (-2 = no previous step, inverse Hessian kept) */
@@ -1518,7 +1518,7 @@ int ntgb_solve_nlp(ntgb_problem *pb, int P, double *C, double *f, double *viol_o
     if (!pb || !C) return fail(NTGB_EINVAL, "ntgb_solve_nlp: null argument");
     if (P <= 0) return 0;
     const ntgb_dims &dm = pb->dims;
-    ntgb_nlp_opts o{40, 80, 1e-6, 1e-6, 10.0, 10.0, 1e-4, 4};
+    ntgb_nlp_opts o{40, 80, 1e-6, 1e-6, 10.0, 10.0, 1e4, 1e-4, 4};
     if (opts) {
         if (opts->max_outer > 0) o.max_outer = opts->max_outer;
         if (opts->max_inner > 0) o.max_inner = opts->max_inner;
@@ -1526,6 +1526,7 @@ int ntgb_solve_nlp(ntgb_problem *pb, int P, double *C, double *f, double *viol_o
         if (opts->ctol > 0.0) o.ctol = opts->ctol;
         if (opts->rho0 > 0.0) o.rho0 = opts->rho0;
         if (opts->rho_mul > 1.0) o.rho_mul = opts->rho_mul;
+        if (opts->rho_max > 0.0) o.rho_max = opts->rho_max;
         if (opts->c1 > 0.0) o.c1 = opts->c1;
         if (opts->check_every > 0) o.check_every = opts->check_every;
     }
@@ -1574,7 +1575,7 @@ int ntgb_solve_nlp(ntgb_problem *pb, int P, double *C, double *f, double *viol_o
         al.ready = true;
     }
     const int nr = al.nr, m = al.m, n_li = al.n_li;
-    constexpr int kNalpha = 12;
+    constexpr int kNalpha = 16;
     const size_t Pz = (size_t)P, Q = Pz * kNalpha;
     const size_t mz = (size_t)std::max(m, 1), ncz = (size_t)std::max(ncnln, 1), nlz = (size_t)std::max(nclin, 1);
     if (Pz > al.cap) {
@@ -1683,7 +1684,7 @@ int ntgb_solve_nlp(ntgb_problem *pb, int P, double *C, double *f, double *viol_o
         /* round finished: fresh multipliers at the point reached, then the outer update */
         if ((rc = assemble())) return rc;
         CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(int), st));
-        CUDA_TRY(launch(k_alm_outer, grid, 128, st, P, m, nr, mu, lam, rho, viol, violp, o.ctol, o.rho_mul,
+        CUDA_TRY(launch(k_alm_outer, grid, 128, st, P, m, nr, mu, lam, rho, viol, violp, o.ctol, o.rho_mul, o.rho_max,
                         outer + 1 == o.max_outer ? 1 : 0, H, state, fails, fin, count));
         int done = 0;
         CUDA_TRY(cudaMemcpyAsync(&done, count, sizeof(int), cudaMemcpyDeviceToHost, st));

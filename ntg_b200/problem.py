@@ -295,8 +295,8 @@ class Problem:
                                     C.addressof(opts), st))
         return f, it, stt
 
-    def solve_nlp(self, Cdev, max_outer=0, max_inner=0, gtol=0.0, ctol=0.0, rho0=0.0, rho_mul=0.0, c1=0.0,
-                  check_every=0):
+    def solve_nlp(self, Cdev, max_outer=0, max_inner=0, gtol=0.0, ctol=0.0, rho0=0.0, rho_mul=0.0, rho_max=0.0,
+                  c1=0.0, check_every=0):
         """batched augmented-Lagrangian solve (ntgb_solve_nlp); Cdev [P][nC] is overwritten.
         Returns f [P], violation [P], iters [P], status [P]."""
         import torch
@@ -306,7 +306,7 @@ class Problem:
         it = torch.zeros(P, dtype=torch.int32, device=Cdev.device)
         stt = torch.zeros(P, dtype=torch.int32, device=Cdev.device)
         opts = NlpOpts(int(max_outer), int(max_inner), float(gtol), float(ctol), float(rho0), float(rho_mul),
-                       float(c1), int(check_every))
+                       float(rho_max), float(c1), int(check_every))
         st = torch.cuda.current_stream(Cdev.device).cuda_stream
         _check(core().ntgb_solve_nlp(self._h, P, Cdev.data_ptr(), f.data_ptr(), v.data_ptr(), it.data_ptr(),
                                      stt.data_ptr(), C.addressof(opts), st))

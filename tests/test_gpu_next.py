@@ -487,3 +487,51 @@ def test_reference_examples_end_to_end_without_npsol(port, example, tmp_path):
         np.testing.assert_allclose(T[-1, :3], [5.0, 40.0, 2.0], atol=1e-3)
         np.testing.assert_allclose(T[[0, -1], 4], [8.0, 8.0], rtol=1e-3)   # speed at both ends
         assert (np.diff(T[:, 1]) > 0).all() and (np.diff(T[:, 2]) >= -1e-6).all()   # a lane change
+
+
+def test_batched_nlp_solver_all_constraint_kinds(port):
+    """ntgb_solve_nlp on the test problem that has EVERY kind of row (packs/endpt.c: initial /
+    trajectory / final cost, nonlinear initial / trajectory / final constraints, linear inequality
+    rows of all three kinds, two outputs with different splines): the assembly of grad L_A from the
+    band Jacobian (k_alm_grad) is only right if the points it stops at are KKT points -- checked by
+    starting scipy SLSQP AT the returned point with the oracle's f, g, c, J: it must stay there."""
+    import torch
+    from scipy.optimize import minimize
+    from ntg_b200 import Problem
+    spec = configs.endpoint()
+    nC = spec.nC
+    P = 64
+    X = np.random.default_rng(3).uniform(-0.5, 0.5, (P, nC))
+    pb = Problem(spec, 0)
+    Cd = torch.from_numpy(X).cuda()
+    f, v, it, st = pb.solve_nlp(Cd, max_outer=60, max_inner=100)
+    Cs, f, v, st = Cd.cpu().numpy(), f.cpu().numpy(), v.cpu().numpy(), st.cpu().numpy()
+    ok = st >= 1
+    assert ok.mean() >= 0.6, f"only {ok.mean():.2f} of the problems converged"
+    o = port.eval(spec, Cs, dense=False, band=False, linear=True)
+    A, bl, bu = o["A"], o["bl"], o["bu"]
+    lbl, ubl = bl[nC:nC + spec.nclin], bu[nC:nC + spec.nclin]
+    lbn, ubn = bl[nC + spec.nclin:], bu[nC + spec.nclin:]
+    lin = Cs @ A.T
+    vl = np.maximum(np.maximum(lbl - lin, lin - ubl), 0).max(axis=1)
+    vn = np.maximum(np.maximum(lbn - o["c"], o["c"] - ubn), 0).max(axis=1)
+    assert (vl[ok] <= 1e-4).all() and (vn[ok] <= 1e-4).all(), (vl[ok].max(), vn[ok].max())
+
+    def fun(c):
+        e = port.eval(spec, c[None, :], mode_obj=2, mode_con=-1, dense=False, band=False)
+        return float(e["f"][0]), e["g"][0]
+
+    def con(c):
+        e = port.eval(spec, c[None, :], mode_obj=-1, mode_con=2, dense=True, band=False)
+        Jd = np.nan_to_num(e["Jdense"][0], nan=0.0)
+        return e["c"][0], (Jd.T if Jd.shape[0] == nC else Jd)
+
+    cons = [{"type": "ineq", "fun": lambda c: A @ c - lbl, "jac": lambda c: A},
+            {"type": "ineq", "fun": lambda c: ubl - A @ c, "jac": lambda c: -A},
+            {"type": "ineq", "fun": lambda c: con(c)[0] - lbn, "jac": lambda c: con(c)[1]},
+            {"type": "ineq", "fun": lambda c: ubn - con(c)[0], "jac": lambda c: -con(c)[1]}]
+    for p in np.flatnonzero(ok)[:3]:
+        r = minimize(fun, Cs[p], jac=True, method="SLSQP", constraints=cons, options={"ftol": 1e-13, "maxiter": 300})
+        assert abs(r.fun - f[p]) <= 1e-4 * max(1.0, abs(f[p])), (r.fun, f[p])
+        assert np.abs(r.x - Cs[p]).max() <= 1e-2, "SLSQP moved away: the returned point was not a KKT point"
+    pb.close()

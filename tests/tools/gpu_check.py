@@ -1,6 +1,6 @@
 """Scratch GPU parity sweep (development aid; the real checks live in tests/)."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from ntg_b200 import configs, Problem, JAC_BAND, JAC_DENSE
 from oracle.oracle import Oracle

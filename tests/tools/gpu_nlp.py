@@ -1,12 +1,12 @@
 """Development aid: batched augmented-Lagrangian solve (ntgb_solve_nlp) on the kinematic-car lane
 change with ACTIVE nonlinear constraints, against scipy SLSQP driven by the CPU oracle.
-Usage: python tools/gpu_nlp.py [P]"""
+Usage: python tests/tools/gpu_nlp.py [P]"""
 import os
 import sys
 import time
 
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
 import numpy as np
 import torch
 from scipy.optimize import minimize

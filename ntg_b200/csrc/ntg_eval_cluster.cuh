@@ -43,7 +43,8 @@ struct ClusterSmem {
     __host__ __device__ size_t fall_off() const { return sc_off() + 4; }                /* [2][nbps] (rank 0) */
     __host__ __device__ size_t t_off() const { return fall_off() + 2 * (size_t)nbps; }  /* [nbps] (rank 0)   */
     __host__ __device__ size_t dt_off() const { return t_off() + nbps; }                /* [nbps]            */
-    __host__ __device__ size_t C_off() const { return dt_off() + nbps; }                /* [2][cwin]         */
+    __host__ __device__ size_t wf_off() const { return dt_off() + nbps; }               /* [nbps] node weights (fast variant) */
+    __host__ __device__ size_t C_off() const { return wf_off() + nbps; }                /* [2][cwin]         */
     __host__ __device__ size_t plan_off() const { return C_off() + 2 * (size_t)cwin; }   /* int2 [plan_n], int [plan_cols+1] */
     __host__ __device__ size_t bytes() const { return (plan_off() + plan_n) * 8 + (size_t)(plan_cols + 2) * 4 + 16; }
 };
@@ -77,6 +78,7 @@ ntg_eval_cluster_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL, int
     double *fall_s = smem + L.fall_off(); /* rank 0 holds the integrand of ALL breakpoints, [buf][nbps] */
     double *t_s = smem + L.t_off();       /* rank 0: trapezoid terms of the scalar cost */
     double *dt_s = smem + L.dt_off();
+    double *wf_s = smem + L.wf_off();     /* (dt[n-1] + dt[n])/2: the trapezoid rule as node weights */
     double *C_s = smem + L.C_off();
     double *fall0 = cluster.map_shared_rank(fall_s, 0);
     double *sc0 = cluster.map_shared_rank(sc_s, 0);
@@ -97,6 +99,11 @@ ntg_eval_cluster_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL, int
 
     /* ---- once per CTA ---- */
     for (int i = threadIdx.x; i < nbps - 1; i += blockDim.x) dt_s[i] = __ldg(T.bps + i + 1) - __ldg(T.bps + i);
+    for (int n = threadIdx.x; n < nbps; n += blockDim.x) {
+        const double lo = n >= 1 ? (__ldg(T.bps + n) - __ldg(T.bps + n - 1)) * 0.5 : 0.0;
+        const double hi = n + 1 < nbps ? (__ldg(T.bps + n + 1) - __ldg(T.bps + n)) * 0.5 : 0.0;
+        wf_s[n] = lo + hi;
+    }
     const int2 *plan = T.plan;
     const int *plan_ptr = T.plan_ptr;
     if (plan_smem) { /* the plan is re-read for every problem: keep it next to the data it indexes */
@@ -429,7 +436,25 @@ ntg_eval_cluster_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL, int
                 double gU[JG], dcur[JG];
 #pragma unroll
                 for (int j = 0; j < JG; j++) { gU[j] = 0.0; dcur[j] = 0.0; }
-                if (doU) {
+                if (doU && !PK::kExact) {
+                    /* fast variant: sum_n Wf[n]*D[n] over the plan's in-band entries (the band is zero at
+                     * both ends of a column's support, so the node-weight form needs no end corrections) */
+                    const int eend = plan_ptr[cl + 1];
+                    for (int e = plan_ptr[cl]; e < eend; e++) {
+                        const int2 en = plan[e];
+                        const int o24 = en.y & 0xffffff, r = en.y >> 24;
+                        if (o24 == 0xffffff) continue;
+                        const double w = wf_s[en.x];
+                        if (r == rank) {
+#pragma unroll
+                            for (int j = 0; j < JG; j++) gU[j] = gU[j] + w * D_s[jbase + j * jpitch + o24];
+                        } else {
+                            const double *base = cluster.map_shared_rank(D_s, r) + jbase + o24;
+#pragma unroll
+                            for (int j = 0; j < JG; j++) gU[j] = gU[j] + w * base[j * jpitch];
+                        }
+                    }
+                } else if (doU) {
                     int e = plan_ptr[cl];
                     const int eend = plan_ptr[cl + 1];
                     if (e < eend) {

@@ -440,6 +440,7 @@ ntg_eval_cluster_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL, int
                     /* fast variant: sum_n Wf[n]*D[n] over the plan's in-band entries (the band is zero at
                      * both ends of a column's support, so the node-weight form needs no end corrections) */
                     const int eend = plan_ptr[cl + 1];
+#pragma unroll 4
                     for (int e = plan_ptr[cl]; e < eend; e++) {
                         const int2 en = plan[e];
                         const int o24 = en.y & 0xffffff, r = en.y >> 24;

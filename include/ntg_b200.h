@@ -155,7 +155,10 @@ int  ntgb_get_dims(const ntgb_problem *pb, ntgb_dims *dims);
 /* device buffers in, device buffers out, asynchronous on args->stream */
 int  ntgb_eval(ntgb_problem *pb, const ntgb_eval_args *args);
 /* same call with HOST buffers: H2D of C, launch, D2H of the requested outputs,
- * synchronous.  This is what ntg()'s funobj/funcon trampolines use. */
+ * synchronous.  This is what ntg()'s funobj/funcon trampolines use.  Large batches are chunked
+ * over two streams so copies overlap the kernels; calls that move less than 256 KB (an NPSOL
+ * callback is P = 1) skip the copies: the kernel reads and writes one page-locked, device-mapped
+ * staging block (NTG_B200_NO_ZEROCOPY=1 forces the copying path). */
 int  ntgb_eval_host(ntgb_problem *pb, const ntgb_eval_args *host_args);
 
 /* Page-locked host memory for ntgb_eval_host (so its copies are asynchronous and overlap the

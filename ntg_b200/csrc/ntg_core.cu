@@ -115,6 +115,16 @@ struct ntgb_problem {
         cudaStream_t stream = nullptr;
     } hs[2];
     int *d_abort = nullptr; /* device flag: a callback wrote *mode = -1 */
+    /* small calls of ntgb_eval_host (an NPSOL callback is P = 1): one page-locked, device-mapped
+     * staging block that the kernel reads its coefficients from and writes its results to -- a
+     * launch and a synchronize instead of eight copies */
+    struct {
+        char *buf = nullptr;
+        size_t bytes = 0;
+        size_t j_off = 0, j_bytes = 0; /* region of the last Jacobian written and its layout */
+        int j_layout = NTGB_JAC_NONE;
+        size_t lastP = 0;
+    } zc;
     std::vector<double> lin_lb, lin_ub; /* expanded linear bounds, [nclin] */
     /* reduced-space data of ntgb_solve_eq: C = C_part + N*y */
     struct {
@@ -773,6 +783,7 @@ void ntgb_destroy(ntgb_problem *pb)
     if (pb->ls.Ct) cudaFree(pb->ls.Ct);
     if (pb->ls.res) cudaFree(pb->ls.res);
     if (pb->ls.lv) cudaFree(pb->ls.lv);
+    if (pb->zc.buf) cudaFreeHost(pb->zc.buf);
     if (pb->alm.blob) cudaFree(pb->alm.blob);
     if (pb->alm.tblob) cudaFree(pb->alm.tblob);
     if (pb->alm.iblob) cudaFree(pb->alm.iblob);
@@ -1238,6 +1249,67 @@ int ntgb_eval(ntgb_problem *pb, const ntgb_eval_args *a)
     return 0;
 }
 
+/* ntgb_eval_host for a handful of problems: everything through one mapped staging block */
+static int eval_host_small(ntgb_problem *pb, const ntgb_eval_args *h, size_t jper)
+{
+    constexpr size_t kBlock = 512 << 10;
+    const ntgb_dims &d = pb->dims;
+    auto &z = pb->zc;
+    if (!z.buf) {
+        CUDA_TRY(cudaHostAlloc((void **)&z.buf, kBlock, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(z.buf, 0, kBlock);
+        z.bytes = kBlock;
+    }
+    auto &s0 = pb->hs[0];
+    if (!s0.stream) CUDA_TRY(cudaStreamCreateWithFlags(&s0.stream, cudaStreamNonBlocking));
+    const size_t P = (size_t)h->P, ncn = (size_t)(d.ncnln > 0 ? d.ncnln : 1);
+    /* fixed carve-up for this P: abort flag, C, f, g, c, result, Z, J (J last: its size depends on the layout) */
+    size_t off = 16;
+    auto take = [&](size_t doubles) { const size_t o = off; off += (doubles * sizeof(double) + 15) & ~(size_t)15; return o; };
+    const size_t oC = take(P * d.nC), of = take(P), og = take(P * d.nC), oc = take(P * ncn), orr = take(P * 2),
+                 oZ = take(h->Z ? P * d.nZ : 0), oJ = take(h->J ? P * jper : 0);
+    if (off > z.bytes) return 1; /* does not fit: the caller falls back to the copying path */
+    if (P != z.lastP) { /* another carve-up: nothing that was written before means anything now */
+        memset(z.buf, 0, z.bytes);
+        z.j_bytes = 0; z.j_layout = NTGB_JAC_NONE; z.lastP = P;
+    }
+    const bool ov = h->mode_obj == 0 || h->mode_obj == 2, od = h->mode_obj == 1 || h->mode_obj == 2;
+    const bool cv = h->mode_con == 0 || h->mode_con == 2, cd = h->mode_con == 1 || h->mode_con == 2;
+    if (h->J && jper) {
+        /* out-of-band entries are zeros written once (src/ntg.c:218); a different layout, batch size
+         * or place in the block means different band positions: clear the old and the new region */
+        if (z.j_layout != h->jac_layout || z.j_off != oJ || z.j_bytes != P * jper * sizeof(double)) {
+            if (z.j_bytes) memset(z.buf + z.j_off, 0, z.j_bytes);
+            memset(z.buf + oJ, 0, P * jper * sizeof(double));
+            z.j_layout = h->jac_layout; z.j_off = oJ; z.j_bytes = P * jper * sizeof(double);
+        }
+    }
+    if (h->Z) memset(z.buf + oZ, 0, P * d.nZ * sizeof(double)); /* entries outside the active-variable lists are 0 */
+    *reinterpret_cast<int *>(z.buf) = 0;
+    memcpy(z.buf + oC, h->C, P * d.nC * sizeof(double));
+    ntgb_eval_args a = *h;
+    a.C = reinterpret_cast<double *>(z.buf + oC);
+    a.f = h->f ? reinterpret_cast<double *>(z.buf + of) : nullptr;
+    a.g = h->g ? reinterpret_cast<double *>(z.buf + og) : nullptr;
+    a.c = h->c ? reinterpret_cast<double *>(z.buf + oc) : nullptr;
+    a.J = h->J ? reinterpret_cast<double *>(z.buf + oJ) : nullptr;
+    a.Z = h->Z ? reinterpret_cast<double *>(z.buf + oZ) : nullptr;
+    a.result = h->result ? reinterpret_cast<double *>(z.buf + orr) : nullptr;
+    a.stream = s0.stream;
+    a.abort_flag = reinterpret_cast<int *>(z.buf);
+    const int rc = ntgb_eval(pb, &a);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s0.stream));
+    if (h->f && ov) memcpy(h->f, z.buf + of, P * sizeof(double));
+    if (h->g && od) memcpy(h->g, z.buf + og, P * d.nC * sizeof(double));
+    if (h->c && cv && d.ncnln) memcpy(h->c, z.buf + oc, P * d.ncnln * sizeof(double));
+    if (h->J && cd && jper) memcpy(h->J, z.buf + oJ, P * jper * sizeof(double));
+    if (h->Z) memcpy(h->Z, z.buf + oZ, P * d.nZ * sizeof(double));
+    if (h->result) memcpy(h->result, z.buf + orr, P * 2 * sizeof(double));
+    if (*reinterpret_cast<volatile int *>(z.buf)) return fail(NTGB_EABORT, "a callback set *mode = -1");
+    return 0;
+}
+
 int ntgb_eval_host(ntgb_problem *pb, const ntgb_eval_args *h)
 {
     if (!pb || !h) return fail(NTGB_EINVAL, "ntgb_eval_host: null argument");
@@ -1254,6 +1326,10 @@ int ntgb_eval_host(ntgb_problem *pb, const ntgb_eval_args *h)
      * for the copies to be asynchronous; pageable memory works, without the overlap. */
     const size_t per = sizeof(double) * ((size_t)2 * d.nC + 3 + (size_t)(d.ncnln > 0 ? d.ncnln : 1) +
                                          (h->J ? jper : 0) + (h->Z ? (size_t)d.nZ : 0));
+    if (per * (size_t)h->P <= (256u << 10) && getenv("NTG_B200_NO_ZEROCOPY") == nullptr) {
+        const int rz = eval_host_small(pb, h, jper);
+        if (rz != 1) return rz; /* 1: did not fit after all */
+    }
     long long chunk = (long long)((64ull << 20) / (per ? per : 1));
     if (chunk < 1024) chunk = 1024;
     if (chunk > h->P) chunk = h->P;

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from common import (GOLDEN_CASES, assert_bitexact, assert_close, golden_spec, load_golden, violation)
-from ntg_b200 import JAC_BAND, JAC_DENSE, configs
+from ntg_b200 import JAC_BAND, JAC_DENSE, JAC_NONE, configs
 
 pytestmark = pytest.mark.gpu
 
@@ -504,4 +504,41 @@ def test_data_dependent_sparsity_falls_back_to_dense(torch_cuda, port, fast):
     # the conditional entries really are non-zero somewhere (otherwise this test proves nothing)
     J = o["Jband"]
     assert np.count_nonzero(o["g"]) > 0 and np.isfinite(J).all()
+    pb.close()
+
+
+def test_eval_host_small_calls_like_npsol(torch_cuda, port, monkeypatch):
+    """Small ntgb_eval_host calls go through one device-mapped staging block (no copies).  NPSOL's
+    pattern -- funobj (f, g) and funcon (c, dense J) alternating at P = 1 -- plus changes of batch
+    size, Jacobian layout and a Z request in between must keep every result equal to the copying
+    path's, INCLUDING the zeros outside the Jacobian band that are only written when a region is
+    first used."""
+    from ntg_b200 import Problem
+    spec, X = golden_spec("endpoint")
+    o = port.eval(spec, X, dense=True, band=True)
+    pb = Problem(spec, 0)
+
+    def check(h, idx, jac, tag):
+        assert_bitexact(h["f"], o["f"][idx], f"{tag}: f")
+        assert_close(h["g"], o["g"][idx], f"{tag}: g")
+        assert_close(h["c"], o["c"][idx], f"{tag}: c")
+        if jac == JAC_DENSE:
+            assert_close(h["J"], np.nan_to_num(o["Jdense"][idx], nan=0.0), f"{tag}: dense J incl. out-of-band zeros")
+        elif jac == JAC_BAND:
+            assert_close(pb.band_to_rows(h["J"]), o["Jband"][idx], f"{tag}: band J")
+
+    seq = [(slice(0, 1), JAC_DENSE), (slice(1, 2), JAC_DENSE), (slice(0, 3), JAC_DENSE), (slice(2, 3), JAC_BAND),
+           (slice(0, 1), JAC_DENSE), (slice(0, 5), JAC_BAND), (slice(3, 4), JAC_DENSE)]
+    for step, (idx, jac) in enumerate(seq):
+        ho = pb.eval_host(X[idx], mode_obj=2, mode_con=-1, jac=JAC_NONE)                 # funobj
+        assert_bitexact(ho["f"], o["f"][idx], f"step {step}: funobj f")
+        h = pb.eval_host(X[idx], mode_obj=2, mode_con=2, jac=jac, want_Z=(step == 3))  # funobj + funcon
+        check(h, idx, jac, f"step {step}")
+    # the copying path gives the same bits
+    monkeypatch.setenv("NTG_B200_NO_ZEROCOPY", "1")
+    h2 = pb.eval_host(X[0:1], jac=JAC_DENSE)
+    monkeypatch.delenv("NTG_B200_NO_ZEROCOPY")
+    h1 = pb.eval_host(X[0:1], jac=JAC_DENSE)
+    for k in ("f", "g", "c", "J"):
+        assert_bitexact(h1[k], h2[k], f"staging block vs copies: {k}")
     pb.close()

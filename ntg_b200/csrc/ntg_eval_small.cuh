@@ -349,6 +349,20 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
     const bool wantZ = !HOT && A.Z != nullptr;
     const bool want_c = HOT || A.c != nullptr;
 
+    /* the first tile's coefficients are requested before anything else: small batches are one tile
+     * per CTA and this latency would otherwise sit behind the table loads below */
+    const int ntiles = (P + GR - 1) / GR;
+    const int tileC = GR * nC; /* doubles of coefficients per tile (contiguous in global memory) */
+    auto stage_C = [&](int tile, int buf) {
+        const long long first = (long long)tile * tileC;
+        const long long total = (long long)P * nC;
+        for (int e = threadIdx.x; e < tileC; e += blockDim.x)
+            if (first + e < total) cp_async8(C_s + (size_t)buf * tileC + e, A.C + first + e);
+        cp_async_commit();
+    };
+    int buf = 0;
+    if ((int)blockIdx.x < ntiles) stage_C(blockIdx.x, 0);
+
     /* ---- once per CTA: dt, offset runs, accumulators; once per thread: its table slice ---- */
     for (int n = threadIdx.x; n < pitch + 2; n += blockDim.x) {
         const double lo = (n >= 1 && n < nbps) ? (__ldg(T.bps + n) - __ldg(T.bps + n - 1)) * 0.5 : 0.0;
@@ -456,17 +470,6 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
         cols_s[c] = use_sched ? __ldg(sched_cols + c) : c;
     }
 
-    const int ntiles = (P + GR - 1) / GR;
-    const int tileC = GR * nC; /* doubles of coefficients per tile (contiguous in global memory) */
-    auto stage_C = [&](int tile, int buf) {
-        const long long first = (long long)tile * tileC;
-        const long long total = (long long)P * nC;
-        for (int e = threadIdx.x; e < tileC; e += blockDim.x)
-            if (first + e < total) cp_async8(C_s + (size_t)buf * tileC + e, A.C + first + e);
-        cp_async_commit();
-    };
-    int buf = 0;
-    if ((int)blockIdx.x < ntiles) stage_C(blockIdx.x, 0);
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
         const int p0 = tile * GR;

@@ -535,3 +535,43 @@ def test_batched_nlp_solver_all_constraint_kinds(port):
         assert abs(r.fun - f[p]) <= 1e-4 * max(1.0, abs(f[p])), (r.fun, f[p])
         assert np.abs(r.x - Cs[p]).max() <= 1e-2, "SLSQP moved away: the returned point was not a KKT point"
     pb.close()
+
+
+def test_solver_edge_cases(port):
+    """P = 1; a problem without any linear constraint (nothing to eliminate: N is the identity);
+    a problem beyond the solvers' limit of 32 free directions is refused, not mangled."""
+    import torch
+    from ntg_b200 import Problem
+    from ntg_b200.problem import NtgError
+    # P = 1 through both solvers
+    spec = configs.vanderpol(20, constraints=False, name="solve_vdp1")
+    pb = Problem(spec, 0)
+    C1 = torch.ones((1, spec.nC), dtype=torch.float64, device="cuda")
+    f, it, st = pb.solve_eq(C1)
+    assert int(st[0]) >= 1
+    C2 = torch.ones((1, spec.nC), dtype=torch.float64, device="cuda")
+    f2, v2, it2, st2 = pb.solve_nlp(C2)
+    assert int(st2[0]) >= 1 and abs(float(f2[0]) - float(f[0])) <= 1e-6 * abs(float(f[0]))
+    pb.close()
+    # no linear constraints at all, one nonlinear trajectory constraint with bounds [-1, 1]
+    spec = configs.high_order(order=6, mult=3, ninterv=4, nbps=33, name="solve_hi")
+    assert spec.nclin == 0
+    pb = Problem(spec, 0)
+    X = np.random.default_rng(8).uniform(-0.5, 0.5, (32, spec.nC))
+    Cd = torch.from_numpy(X).cuda()
+    f, v, it, st = pb.solve_nlp(Cd)
+    Cs = Cd.cpu().numpy()
+    o = port.eval(spec, Cs, mode_obj=2, mode_con=0, dense=False, band=False)
+    assert_close(f.cpu().numpy(), o["f"], "cost at the returned point")
+    ok = st.cpu().numpy() >= 1
+    assert ok.mean() >= 0.9
+    assert (np.abs(o["c"][ok]).max(axis=1) <= 1.0 + 1e-5).all()
+    # the cost is a positive definite quadratic and C = 0 is feasible: the minimum is f = 0 at C = 0
+    assert (f.cpu().numpy()[ok] <= 1e-8).all()
+    pb.close()
+    # too many free directions
+    spec, _ = configs.get("cfg5")
+    pb = Problem(spec, 0)
+    with pytest.raises(NtgError):
+        pb.solve_nlp(torch.zeros((2, spec.nC), dtype=torch.float64, device="cuda"))
+    pb.close()

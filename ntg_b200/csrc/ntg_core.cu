@@ -578,12 +578,12 @@ __device__ __forceinline__ double alm_row(double h, double lam, double rho, doub
  * multipliers (optional), augmented Lagrangian value, scaled violation */
 __global__ void k_alm_mu(int Q, int nalpha, int ncnln, int nclin, int n_li, const int *li_idx, const double *hl,
                          const double *hu, const double *lam, const double *rho, const double *f, const double *c,
-                         const double *lin, double *mu, double *LA, double *viol, int LAstride)
+                         const double *lin, double *mu, double *LA, double *viol, int LAstride, const int *pidx)
 {
     const int q = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (q >= Q) return;
-    const int p = q / nalpha;
+    const int p = pidx != nullptr ? pidx[q / nalpha] : q / nalpha;
     const int m = n_li + ncnln;
     const double r = rho[p];
     double acc = 0.0, vmax = 0.0;
@@ -682,6 +682,63 @@ __global__ void k_alm_prep(int P, int m, double rho0, double *lam, double *rho, 
     rho[p] = rho0;
     violprev[p] = 1e300;
     fin[p] = 0;
+}
+
+/* two-stage line search of ntgb_solve_nlp: the coarse steps are tried for every problem, the fine
+ * ones only for the problems (listed in idx) that found no Armijo step among them */
+__global__ void k_ls_trial_idx(const double *C, const double *dC, const double *alpha, const int *idx, int n, int nalpha,
+                               int nC, double *Ct)
+{
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)n * nalpha * nC;
+    if (q >= total) return;
+    const int e = (int)(q % nC);
+    const long long ia = q / nC;
+    const int a = (int)(ia % nalpha);
+    const long long p = idx[ia / nalpha];
+    Ct[q] = C[p * nC + e] + alpha[a] * dC[p * nC + e];
+}
+
+/* stage 1: first coarse alpha with Armijo decrease, else the best one seen; problems without an
+ * Armijo step (and still running) are appended to idx */
+__global__ void k_alm_pick1(const double *res, const double *alpha, int P, int nalpha, double c1, const double *phi0,
+                            const double *dphi0, const int *state, double *alpha_best, double *phi_best, int *idx,
+                            int *nidx)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    int best = 0, chosen = -1;
+    double phib = 0.0;
+    for (int a = 0; a < nalpha; a++) {
+        const double phi = res[2 * ((size_t)p * nalpha + a)];
+        if (a == 0 || phi < phib) { phib = phi; best = a; }
+        if (chosen < 0 && phi <= phi0[p] + c1 * alpha[a] * dphi0[p]) chosen = a;
+    }
+    const int pick = chosen >= 0 ? chosen : best;
+    alpha_best[p] = alpha[pick];
+    phi_best[p] = res[2 * ((size_t)p * nalpha + pick)];
+    if (chosen < 0 && state[p] == 0) idx[atomicAdd(nidx, 1)] = p;
+}
+
+/* stage 2: the fine alphas of the listed problems */
+__global__ void k_alm_pick2(const double *res, const double *alpha, const int *idx, int n, int nalpha, double c1,
+                            const double *phi0, const double *dphi0, double *alpha_best, double *phi_best)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int p = idx[i];
+    int best = -1, chosen = -1;
+    double phib = phi_best[p];
+    for (int a = 0; a < nalpha; a++) {
+        const double phi = res[2 * ((size_t)i * nalpha + a)];
+        if (phi < phib) { phib = phi; best = a; }
+        if (chosen < 0 && phi <= phi0[p] + c1 * alpha[a] * dphi0[p]) chosen = a;
+    }
+    const int pick = chosen >= 0 ? chosen : best;
+    if (pick >= 0) {
+        alpha_best[p] = alpha[pick];
+        phi_best[p] = res[2 * ((size_t)i * nalpha + pick)];
+    }
 }
 
 int check_avs(const AV *av, int n, const ntgb_setup *s, const char *what)
@@ -1651,7 +1708,7 @@ int ntgb_solve_nlp(ntgb_problem *pb, int P, double *C, double *f, double *viol_o
         al.ready = true;
     }
     const int nr = al.nr, m = al.m, n_li = al.n_li;
-    constexpr int kNalpha = 16;
+    constexpr int kN1 = 4, kN2 = 12, kNalpha = kN1 + kN2;
     const size_t Pz = (size_t)P, Q = Pz * kNalpha;
     const size_t mz = (size_t)std::max(m, 1), ncz = (size_t)std::max(ncnln, 1), nlz = (size_t)std::max(nclin, 1);
     if (Pz > al.cap) {
@@ -1664,7 +1721,7 @@ int ntgb_solve_nlp(ntgb_problem *pb, int P, double *C, double *f, double *viol_o
         const size_t nt = Q * ((size_t)nC + ncz + nlz + 4);
         CUDA_TRY(cudaMalloc((void **)&al.blob, nd * sizeof(double)));
         CUDA_TRY(cudaMalloc((void **)&al.tblob, nt * sizeof(double)));
-        CUDA_TRY(cudaMalloc((void **)&al.iblob, ((size_t)4 * P + 1) * sizeof(int)));
+        CUDA_TRY(cudaMalloc((void **)&al.iblob, ((size_t)5 * P + 2) * sizeof(int)));
         al.cap = Pz;
     }
     const size_t cap = al.cap;
@@ -1699,7 +1756,8 @@ int ntgb_solve_nlp(ntgb_problem *pb, int P, double *C, double *f, double *viol_o
     double *lint = t;   t += capq * nlz;
     double *ft = t;     t += capq;
     double *res = t;    /* [Q][2] */
-    int *state = al.iblob, *its = state + cap, *fails = its + cap, *fin = fails + cap, *count = fin + cap;
+    int *state = al.iblob, *its = state + cap, *fails = its + cap, *fin = fails + cap, *idx = fin + cap, *count = idx + cap,
+        *nidx = count + 1;
 
     double ha[kNalpha];
     for (int a = 0; a < kNalpha; a++) ha[a] = std::ldexp(1.0, -a);
@@ -1726,7 +1784,7 @@ int ntgb_solve_nlp(ntgb_problem *pb, int P, double *C, double *f, double *viol_o
         if (n_li > 0 && (r2 = ntgb_eval_linear(pb, P, C, lin, nullptr, st))) return r2;
         const unsigned gw = (unsigned)(((long long)P * 32 + 127) / 128);
         CUDA_TRY(launch(k_alm_mu, gw, 128, st, P, 1, ncnln, nclin, n_li, al.li_idx, al.hl, al.hu, lam, rho, fv, cc, lin, mu,
-                        LA, viol, 1));
+                        LA, viol, 1, (const int *)nullptr));
         const long long tot = (long long)P * nC;
         CUDA_TRY(launch(k_alm_grad, (unsigned)((tot + 127) / 128), 128, st, P, pb->tab, nclin, n_li, al.li_idx, al.A, g, J,
                         mu, gA));
@@ -1744,16 +1802,36 @@ int ntgb_solve_nlp(ntgb_problem *pb, int P, double *C, double *f, double *viol_o
                 CUDA_TRY(cudaStreamSynchronize(st));
                 if (done >= P) break;
             }
-            /* Armijo line search on the augmented Lagrangian: P*12 trial points in one evaluation */
-            const long long totc = (long long)Q * nC;
-            CUDA_TRY(launch(k_ls_trial, (unsigned)((totc + 255) / 256), 256, st, C, dC, alphas, P, kNalpha, nC, Ct));
-            if ((rc = ntgb_eval(pb, &et))) return rc;
-            if (n_li > 0 && (rc = ntgb_eval_linear(pb, (int)Q, Ct, lint, nullptr, st))) return rc;
-            const unsigned gq = (unsigned)(((long long)Q * 32 + 127) / 128);
-            CUDA_TRY(launch(k_alm_mu, gq, 128, st, (int)Q, kNalpha, ncnln, nclin, n_li, al.li_idx, al.hl, al.hu, lam, rho, ft,
-                            ct, lint, (double *)nullptr, res, (double *)nullptr, 2));
-            CUDA_TRY(launch(k_ls_pick, grid, 128, st, res, (const double *)nullptr, alphas, P, kNalpha, 0.0, o.c1, phi0, dphi0,
-                            C, dC, nC, ab, pbest, (double *)nullptr));
+            /* Armijo line search on the augmented Lagrangian, two stages: the steps 1 .. 1/8 for every
+             * problem in one evaluation; the steps 2^-4 .. 2^-15 only for the problems that found
+             * no Armijo step among them (compacted by index), in a second one */
+            {
+                const long long totc = (long long)P * kN1 * nC;
+                CUDA_TRY(launch(k_ls_trial, (unsigned)((totc + 255) / 256), 256, st, C, dC, alphas, P, kN1, nC, Ct));
+                et.P = P * kN1;
+                if ((rc = ntgb_eval(pb, &et))) return rc;
+                if (n_li > 0 && (rc = ntgb_eval_linear(pb, et.P, Ct, lint, nullptr, st))) return rc;
+                const unsigned gq = (unsigned)(((long long)et.P * 32 + 127) / 128);
+                CUDA_TRY(launch(k_alm_mu, gq, 128, st, et.P, kN1, ncnln, nclin, n_li, al.li_idx, al.hl, al.hu, lam, rho, ft, ct,
+                                lint, (double *)nullptr, res, (double *)nullptr, 2, (const int *)nullptr));
+                CUDA_TRY(cudaMemsetAsync(nidx, 0, sizeof(int), st));
+                CUDA_TRY(launch(k_alm_pick1, grid, 128, st, res, alphas, P, kN1, o.c1, phi0, dphi0, state, ab, pbest, idx, nidx));
+                int n2 = 0;
+                CUDA_TRY(cudaMemcpyAsync(&n2, nidx, sizeof(int), cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+                if (n2 > 0) {
+                    const long long tot2 = (long long)n2 * kN2 * nC;
+                    CUDA_TRY(launch(k_ls_trial_idx, (unsigned)((tot2 + 255) / 256), 256, st, C, dC, alphas + kN1, idx, n2, kN2, nC, Ct));
+                    et.P = n2 * kN2;
+                    if ((rc = ntgb_eval(pb, &et))) return rc;
+                    if (n_li > 0 && (rc = ntgb_eval_linear(pb, et.P, Ct, lint, nullptr, st))) return rc;
+                    const unsigned g2 = (unsigned)(((long long)et.P * 32 + 127) / 128);
+                    CUDA_TRY(launch(k_alm_mu, g2, 128, st, et.P, kN2, ncnln, nclin, n_li, al.li_idx, al.hl, al.hu, lam, rho, ft,
+                                    ct, lint, (double *)nullptr, res, (double *)nullptr, 2, idx));
+                    CUDA_TRY(launch(k_alm_pick2, (unsigned)((n2 + 127) / 128), 128, st, res, alphas + kN1, idx, n2, kN2, o.c1, phi0,
+                                    dphi0, ab, pbest));
+                }
+            }
             CUDA_TRY(launch(k_solve_update, grid, 128, st, P, nC, nr, al.N, al.Cpart, phi0, ab, pbest, d, y, H, C, state, its,
                             fails, count));
         }

@@ -245,7 +245,8 @@ int  ntgb_solve_eq(ntgb_problem *pb, int P, double *C, double *f, int *iters, in
  * bounds) that is minimised per problem by the same reduced-space BFGS, multipliers and penalty
  * updated between rounds.  Every step is a batched kernel: evaluation with the band Jacobian,
  * multiplier / merit kernel, J^T*mu gather per gradient column, BFGS direction, batched Armijo line
- * search (16 halvings, all trial points in one evaluation) on the augmented Lagrangian.  C [P][nC] (device): guesses in, solutions out.  f, viol
+ * search on the augmented Lagrangian (steps 1 .. 1/8 for every problem in one evaluation, steps
+ * 2^-4 .. 2^-15 in a second one for the compacted list of problems that need them).  C [P][nC] (device): guesses in, solutions out.  f, viol
  * (maximum violation of any constraint), iters (evaluations of the inner loop), status
  * (1 = violation <= ctol and reduced gradient <= gtol, 2 = violation <= ctol and no further
  * decrease of the merit function possible, 0 = not converged) are optional device outputs.

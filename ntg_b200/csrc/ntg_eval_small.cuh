@@ -143,19 +143,18 @@ __device__ __forceinline__ double nl_bound(const ntgb_devtab &T, bool upper, int
 }
 
 /* Trapezoid quadrature of one run of a band row (src/integrator.c:21-24, :44-48).  row[n] is the
- * band value at breakpoint n (16-byte aligned at even n), wt[n] = (t[n]-t[n-1])/2.
+ * band value at breakpoint n (16-byte aligned at even n), dt[n] = t[n]-t[n-1].
  *
- * trap_run_exact: terms n0..n1, g = g + wt[n]*(row[n] + row[n-1]) one after the other in ascending
- * order -- the reference's operation order ((dt*(a+b))/2 with the exact halving moved into the
- * weight: identical bits unless a term underflows below 2.2e-308).  The terms do not depend on the
- * running sum, so they are computed four at a time ahead of the additions. */
+ * trap_run_exact: terms n0..n1, g = g + (dt[n]*(row[n] + row[n-1]))/2 one after the other in
+ * ascending order -- the reference's expression and operation order.  The terms do not depend on
+ * the running sum, so they are computed four at a time ahead of the additions. */
 __device__ __forceinline__ void trap_run_exact(const double *row, const double *wt, int n0, int n1, double &prev,
                                                double &g)
 {
     int n = n0;
     if ((n & 1) && n <= n1) {
         const double d = row[n];
-        g = g + wt[n] * (d + prev);
+        g = g + (wt[n] * (d + prev)) / 2;
         prev = d;
         n++;
     }
@@ -164,8 +163,8 @@ __device__ __forceinline__ void trap_run_exact(const double *row, const double *
          * dependent additions */
         double2 d01 = *reinterpret_cast<const double2 *>(row + n), d23 = *reinterpret_cast<const double2 *>(row + n + 2);
         double2 w01 = *reinterpret_cast<const double2 *>(wt + n), w23 = *reinterpret_cast<const double2 *>(wt + n + 2);
-        double t0 = w01.x * (d01.x + prev), t1 = w01.y * (d01.y + d01.x), t2 = w23.x * (d23.x + d01.y),
-               t3 = w23.y * (d23.y + d23.x);
+        double t0 = (w01.x * (d01.x + prev)) / 2, t1 = (w01.y * (d01.y + d01.x)) / 2, t2 = (w23.x * (d23.x + d01.y)) / 2,
+               t3 = (w23.y * (d23.y + d23.x)) / 2;
         prev = d23.y;
         n += 4;
         for (; n + 3 <= n1; n += 4) {
@@ -173,8 +172,8 @@ __device__ __forceinline__ void trap_run_exact(const double *row, const double *
             d23 = *reinterpret_cast<const double2 *>(row + n + 2);
             w01 = *reinterpret_cast<const double2 *>(wt + n);
             w23 = *reinterpret_cast<const double2 *>(wt + n + 2);
-            const double u0 = w01.x * (d01.x + prev), u1 = w01.y * (d01.y + d01.x), u2 = w23.x * (d23.x + d01.y),
-                         u3 = w23.y * (d23.y + d23.x);
+            const double u0 = (w01.x * (d01.x + prev)) / 2, u1 = (w01.y * (d01.y + d01.x)) / 2,
+                         u2 = (w23.x * (d23.x + d01.y)) / 2, u3 = (w23.y * (d23.y + d23.x)) / 2;
             prev = d23.y;
             g = g + t0;
             g = g + t1;
@@ -189,7 +188,7 @@ __device__ __forceinline__ void trap_run_exact(const double *row, const double *
     }
     for (; n <= n1; n++) {
         const double d = row[n];
-        g = g + wt[n] * (d + prev);
+        g = g + (wt[n] * (d + prev)) / 2;
         prev = d;
     }
 }
@@ -324,7 +323,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
     double *cI_s = smem + L.cI_off();
     double *cF_s = smem + L.cF_off();
     double *viol_s = smem + L.viol_off();
-    double *wt_s = smem + L.dt_off();  /* wt[n] = (t[n]-t[n-1])/2, wt[0] = 0 */
+    double *wt_s = smem + L.dt_off();  /* exact variant: dt[n] = t[n]-t[n-1] (dt[0] = 0); the fast one only uses Wf */
     double *Wf_s = wt_s + pitch + 2;   /* node weights wt[n] + wt[n+1] */
     double *C_s = smem + L.C_off();
     int *segstart_s = reinterpret_cast<int *>(smem + L.seg_off());
@@ -367,7 +366,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
     for (int n = threadIdx.x; n < pitch + 2; n += blockDim.x) {
         const double lo = (n >= 1 && n < nbps) ? (__ldg(T.bps + n) - __ldg(T.bps + n - 1)) * 0.5 : 0.0;
         const double hi = (n + 1 < nbps) ? (__ldg(T.bps + n + 1) - __ldg(T.bps + n)) * 0.5 : 0.0;
-        wt_s[n] = lo;
+        wt_s[n] = (n >= 1 && n < nbps) ? __ldg(T.bps + n) - __ldg(T.bps + n - 1) : 0.0;
         Wf_s[n] = lo + hi;
     }
     {
@@ -705,7 +704,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                             if ((unsigned)k < order) {
                                 trap_run_exact(Dj + (size_t)k * rowp, wt_s, n, segend, dcur, gU);
                             } else { /* leaving the band: one term against an exact zero, the rest are zeros */
-                                gU = gU + wt_s[n] * (0.0 + dcur);
+                                gU = gU + (wt_s[n] * (0.0 + dcur)) / 2;
                                 dcur = 0.0;
                             }
                             n = segend + 1;

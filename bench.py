@@ -486,6 +486,13 @@ def main():
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        # The persistent evaluator fills every SM, so a co-running NCCL kernel could only start when
+        # evaluator CTAs retire and would then hold back a few CTAs of the NEXT launch, which finish
+        # last (+13 us per step at N = 2).  Four SMs are left free and the all-gather of the 16 B/problem
+        # result table is limited to four channels (one CTA each): it then truly overlaps the next
+        # kernel (measured at N = 2: 144 -> 139 us per step).
+        os.environ.setdefault("NTG_B200_SM_RESERVE", "4")
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "4")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from ntg_b200 import Problem

@@ -928,6 +928,13 @@ int ntgb_create(ntgb_problem **out, const ntgb_setup *s, int device)
     } cleanup{pb};
 
     CUDA_TRY(cudaDeviceGetAttribute(&pb->sm_count, cudaDevAttrMultiProcessorCount, device));
+    /* The persistent evaluators fill every SM (registers and shared memory).  When another kernel
+     * must run beside them -- the NCCL all-gather of the result tables in a multi-GPU job -- a few
+     * SMs left free keep it from delaying a handful of evaluator CTAs, which would finish last. */
+    if (const char *e = getenv("NTG_B200_SM_RESERVE")) {
+        const int r = atoi(e);
+        if (r > 0 && r < pb->sm_count) pb->sm_count -= r;
+    }
     CUDA_TRY(cudaDeviceGetAttribute(&pb->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
 
     ntgb_devtab &T = pb->tab;

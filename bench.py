@@ -486,13 +486,15 @@ def main():
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
-        # The persistent evaluator fills every SM, so a co-running NCCL kernel could only start when
-        # evaluator CTAs retire and would then hold back a few CTAs of the NEXT launch, which finish
-        # last (+13 us per step at N = 2).  Four SMs are left free and the all-gather of the 16 B/problem
-        # result table is limited to four channels (one CTA each): it then truly overlaps the next
-        # kernel (measured at N = 2: 144 -> 139 us per step).
-        os.environ.setdefault("NTG_B200_SM_RESERVE", "4")
-        os.environ.setdefault("NCCL_MAX_NCHANNELS", "4")
+        # The persistent evaluator fills every SM, so a co-running NCCL kernel can only start when
+        # evaluator CTAs retire and then holds back a few CTAs of the NEXT launch, which finish last.
+        # Measured per step (65 536 problems per GPU): N = 2, NCCL defaults 144 us; four SMs left free
+        # and the all-gather of the 16 B/problem table limited to four channels 139 us.  At N = 4
+        # and 8 the gathered table is 4 / 8 MB and needs NCCL's default channel count (138 / 149 us;
+        # four channels: 234 / 386 us), so the limit is applied to two ranks only.
+        if world == 2:
+            os.environ.setdefault("NTG_B200_SM_RESERVE", "4")
+            os.environ.setdefault("NCCL_MAX_NCHANNELS", "4")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from ntg_b200 import Problem

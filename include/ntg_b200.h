@@ -134,7 +134,19 @@ typedef struct ntgb_eval_args {
                           * writing *mode = -1 (reference src/ntg.c:369: NPSOL then terminates);
                           * the caller zeroes it.  ntgb_eval_host manages its own and returns
                           * NTGB_EABORT.                                        */
+    /* Fused multi-GPU gather (optional; npeers = 0 turns it off).  Problems are sharded over the
+     * GPUs of a node and the only thing the ranks exchange is the 16 B/problem (objective,
+     * violation) table.  Instead of a collective after the kernel, the evaluator's epilogue stores
+     * each pair into EVERY rank's copy of the gathered table -- peer_result[r] is rank r's table
+     * [total problems][2], mapped into this process (ntgb_peer_table_open: CUDA IPC, NVLink peer
+     * stores); this rank's rows start at peer_row0.  No NCCL kernel competes with the persistent
+     * evaluator for SMs.  A rank may read its table once every rank's stream has been
+     * synchronised (a barrier), exactly when it could have waited for an asynchronous collective. */
+    int npeers;
+    int peer_row0;
+    double *peer_result[8]; /* NTGB_MAXPEERS */
 } ntgb_eval_args;
+#define NTGB_MAXPEERS 8
 
 /* error codes */
 #define NTGB_OK        0
@@ -266,6 +278,15 @@ typedef struct ntgb_nlp_opts {
 } ntgb_nlp_opts;
 int  ntgb_solve_nlp(ntgb_problem *pb, int P, double *C, double *f, double *viol, int *iters, int *status,
                     const ntgb_nlp_opts *opts, void *stream);
+
+/* Gathered result tables for the fused multi-GPU gather (ntgb_eval_args.peer_result): alloc creates
+ * this rank's table (rows x 2 doubles, zeroed) and the 64-byte CUDA IPC handle the other ranks
+ * need; open maps another rank's table into this process (peer access over NVLink is enabled on
+ * first use); close unmaps it; free releases an own table. */
+int  ntgb_peer_table_alloc(ntgb_problem *pb, size_t rows, double **table, unsigned char handle[64]);
+int  ntgb_peer_table_open(ntgb_problem *pb, const unsigned char handle[64], double **table);
+int  ntgb_peer_table_close(ntgb_problem *pb, double *table);
+int  ntgb_peer_table_free(ntgb_problem *pb, double *table);
 
 /* ---- callback packs ------------------------------------------------------ */
 /*

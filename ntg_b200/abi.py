@@ -74,6 +74,9 @@ class NtgbEvalArgs(C.Structure):
         ("result", C.c_void_p),
         ("stream", C.c_void_p),
         ("abort_flag", C.c_void_p),
+        ("npeers", C.c_int),
+        ("peer_row0", C.c_int),
+        ("peer_result", C.c_void_p * 8),
     ]
 
 

@@ -1299,6 +1299,10 @@ int ntgb_eval(ntgb_problem *pb, const ntgb_eval_args *a)
         return fail(NTGB_EINVAL, "mode must be -1, 0, 1 or 2");
     if (a->jac_layout < NTGB_JAC_NONE || a->jac_layout > NTGB_JAC_BAND)
         return fail(NTGB_EINVAL, "unknown jac_layout %d", a->jac_layout);
+    if (a->npeers < 0 || a->npeers > NTGB_MAXPEERS || a->peer_row0 < 0)
+        return fail(NTGB_EINVAL, "npeers = %d outside [0,%d] or negative peer_row0", a->npeers, NTGB_MAXPEERS);
+    for (int r = 0; r < a->npeers; r++)
+        if (!a->peer_result[r]) return fail(NTGB_EINVAL, "peer_result[%d] == NULL", r);
     DeviceGuard dg(pb->device);
     if (!dg.ok) return fail(NTGB_ECUDA, "cannot select device %d", pb->device);
     ntgb_launch L;
@@ -1857,6 +1861,55 @@ int ntgb_solve_nlp(ntgb_problem *pb, int P, double *C, double *f, double *viol_o
     if (iters) CUDA_TRY(cudaMemcpyAsync(iters, its, sizeof(int) * Pz, cudaMemcpyDeviceToDevice, st));
     if (status) CUDA_TRY(cudaMemcpyAsync(status, fin, sizeof(int) * Pz, cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int ntgb_peer_table_alloc(ntgb_problem *pb, size_t rows, double **table, unsigned char handle[64])
+{
+    if (!pb || !table || !handle || rows == 0) return fail(NTGB_EINVAL, "ntgb_peer_table_alloc: bad argument");
+    DeviceGuard dg(pb->device);
+    if (!dg.ok) return fail(NTGB_ECUDA, "cannot select device %d", pb->device);
+    double *p = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&p, rows * 2 * sizeof(double)));
+    CUDA_TRY(cudaMemset(p, 0, rows * 2 * sizeof(double)));
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(h) == 64, "CUDA IPC handles are 64 bytes");
+    const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail(NTGB_ECUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle, &h, 64);
+    *table = p;
+    return 0;
+}
+
+int ntgb_peer_table_open(ntgb_problem *pb, const unsigned char handle[64], double **table)
+{
+    if (!pb || !table || !handle) return fail(NTGB_EINVAL, "ntgb_peer_table_open: null argument");
+    DeviceGuard dg(pb->device);
+    if (!dg.ok) return fail(NTGB_ECUDA, "cannot select device %d", pb->device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void *p = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *table = static_cast<double *>(p);
+    return 0;
+}
+
+int ntgb_peer_table_close(ntgb_problem *pb, double *table)
+{
+    if (!pb || !table) return 0;
+    DeviceGuard dg(pb->device);
+    CUDA_TRY(cudaIpcCloseMemHandle(table));
+    return 0;
+}
+
+int ntgb_peer_table_free(ntgb_problem *pb, double *table)
+{
+    if (!pb || !table) return 0;
+    DeviceGuard dg(pb->device);
+    CUDA_TRY(cudaFree(table));
     return 0;
 }
 

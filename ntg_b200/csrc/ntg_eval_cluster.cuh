@@ -192,9 +192,9 @@ ntg_eval_cluster_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL, int
             }
             const double y = (sc_s[b * 2 + 0] + In) + sc_s[b * 2 + 1]; /* y = I + In + F, src/ntg.c:303,328 */
             if (obj_v && A.f != nullptr) A.f[pp] = y;
-            if (A.result != nullptr) {
-                A.result[2 * (size_t)pp] = obj_v ? y : 0.0;
-                A.result[2 * (size_t)pp + 1] = __longlong_as_double((long long)vb);
+            if (want_result(A)) {
+                put_result(A, (size_t)pp, 0, obj_v ? y : 0.0);
+                put_result(A, (size_t)pp, 1, __longlong_as_double((long long)vb));
             }
         }
         __syncwarp();

@@ -62,6 +62,15 @@ __host__ __device__ constexpr int pk_nz() { return pk_iz<PK>(PK::kNout); }
 
 __device__ __forceinline__ void st_stream(double *p, double v) { __stcs(p, v); }
 
+/* one entry (which = 0 objective, 1 violation) of problem p's result pair: the local table and, for
+ * the fused multi-GPU gather, every rank's copy of the gathered table (peer stores over NVLink) */
+__device__ __forceinline__ void put_result(const ntgb_eval_args &A, size_t p, int which, double v)
+{
+    if (A.result != nullptr) A.result[2 * p + which] = v;
+    for (int r = 0; r < A.npeers; r++) A.peer_result[r][2 * ((size_t)A.peer_row0 + p) + which] = v;
+}
+__device__ __forceinline__ bool want_result(const ntgb_eval_args &A) { return A.result != nullptr || A.npeers > 0; }
+
 /* a callback that writes *mode = -1 asks the solver to stop (reference src/ntg.c:369) */
 __device__ __forceinline__ void note_abort(const ntgb_eval_args &A, int mode)
 {
@@ -373,7 +382,7 @@ __global__ void __launch_bounds__(256) ntg_eval_kernel(const ntgb_devtab T, cons
             if (c == nC) {
                 /* scalar cost: IntegrateVector TRAPEZOID, src/integrator.c:21-24, then
                  * y = I + In + F, src/ntg.c:303,328 */
-                if (obj_v || A.result != nullptr) {
+                if (obj_v || want_result(A)) {
                     double In = 0.0;
                     if (doU && obj_v) {
                         const double *fp = f_s + (size_t)pl * nbps;
@@ -387,9 +396,9 @@ __global__ void __launch_bounds__(256) ntg_eval_kernel(const ntgb_devtab T, cons
                     }
                     const double y = (cI_s[pl] + In) + cF_s[pl];
                     if (obj_v && A.f != nullptr) A.f[p] = y;
-                    if (A.result != nullptr) {
-                        A.result[2 * (size_t)p] = obj_v ? y : 0.0;
-                        A.result[2 * (size_t)p + 1] = __longlong_as_double((long long)viol_s[pl]);
+                    if (want_result(A)) {
+                        put_result(A, (size_t)p, 0, obj_v ? y : 0.0);
+                        put_result(A, (size_t)p, 1, __longlong_as_double((long long)viol_s[pl]));
                     }
                 }
                 continue;

@@ -54,6 +54,10 @@ def core() -> C.CDLL:
         lib.ntgb_solve_nlp.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]
         lib.ntgb_solve_nlp.restype = C.c_int
+        lib.ntgb_peer_table_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]
+        lib.ntgb_peer_table_open.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
+        lib.ntgb_peer_table_close.argtypes = [C.c_void_p, C.c_void_p]
+        lib.ntgb_peer_table_free.argtypes = [C.c_void_p, C.c_void_p]
         lib.ntgb_linesearch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                         C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]
@@ -175,7 +179,9 @@ class Problem:
         return out
 
     def eval_args(self, Cdev, out, mode_obj=2, mode_con=2, jac=JAC_BAND, nstate=0, stream=None,
-                  abort_flag=None) -> NtgbEvalArgs:
+                  abort_flag=None, peers=None) -> NtgbEvalArgs:
+        """peers: a shard.PeerGather -- the kernel then also stores every (objective, violation) pair
+        into all ranks' gathered tables (fused multi-GPU gather)"""
         a = NtgbEvalArgs()
         a.P = int(Cdev.shape[0])
         a.C = Cdev.data_ptr()
@@ -187,6 +193,11 @@ class Problem:
         a.result = _ptr(out.get("result"))
         a.stream = stream
         a.abort_flag = _ptr(abort_flag)
+        if peers is not None:
+            a.npeers = len(peers.tables)
+            a.peer_row0 = peers.row0
+            for r, t in enumerate(peers.tables):
+                a.peer_result[r] = t
         return a
 
     def launch(self, args: NtgbEvalArgs):

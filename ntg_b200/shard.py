@@ -4,7 +4,8 @@ Problems are independent (they share only read-only tables), so there is no
 data-path collective: rank r of R owns the contiguous slice
 [r*P/R, (r+1)*P/R).  The only exchange is the per-problem
 result table (objective, max constraint violation) = 16 B/problem, gathered
-with one all_gather over NCCL (NVLink/NVSwitch) -- or gloo in the CPU tests.
+with one all_gather over NCCL (NVLink/NVSwitch) -- or gloo in the CPU tests --
+or, fused into the evaluator, by peer stores into every rank's table (PeerGather).
 """
 from __future__ import annotations
 
@@ -46,3 +47,66 @@ def gather_results(local, P: int, group=None):
     buf = torch.empty((world * m, local.shape[1]), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(buf, pad, group=group)
     return torch.cat([buf[r * m: r * m + sizes[r]] for r in range(world)], dim=0)
+
+
+class PeerGather:
+    """Fused multi-GPU gather: every rank owns one gathered table [P_total][2] in its HBM; the
+    tables of the other ranks are mapped into this process with CUDA IPC (ntgb_peer_table_open)
+    and the evaluator's epilogue stores each (objective, violation) pair into ALL of them over
+    NVLink -- no collective kernel runs beside the persistent evaluator.  Ranks must be on one node
+    with peer access (NVSwitch).  `table()` is this rank's copy; read it after `fence()`."""
+
+    def __init__(self, pb, P_total: int, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from .problem import _check, core
+        self.pb, self.P_total, self.group = pb, int(P_total), group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise ValueError("PeerGather: at most 8 ranks (NTGB_MAXPEERS)")
+        self.row0 = shard_range(self.P_total, self.rank, self.world)[0]
+        own = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        _check(core().ntgb_peer_table_alloc(pb._h, self.P_total, C.byref(own), handle))
+        self._own = own.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self.tables, self._opened = [], []
+        for r in range(self.world):
+            if r == self.rank:
+                self.tables.append(self._own)
+                continue
+            ptr = C.c_void_p()
+            _check(core().ntgb_peer_table_open(pb._h, handles[r], C.byref(ptr)))
+            self.tables.append(ptr.value)
+            self._opened.append(ptr.value)
+        dist.barrier(group=group)
+        self._torch = torch
+
+    def table(self):
+        """this rank's gathered table as a [P_total][2] float64 cuda tensor (a view, no copy)"""
+        class _View:
+            pass
+        v = _View()
+        v.__cuda_array_interface__ = {"shape": (self.P_total, 2), "typestr": "<f8", "data": (self._own, False),
+                                      "version": 2, "strides": None}
+        return self._torch.as_tensor(v, device=f"cuda:{self.pb.device}")
+
+    def fence(self):
+        """every rank's evaluator launches so far have completed: the tables are consistent"""
+        import torch.distributed as dist
+        self._torch.cuda.synchronize(self.pb.device)
+        dist.barrier(group=self.group)
+
+    def close(self):
+        from .problem import core
+        import torch.distributed as dist
+        dist.barrier(group=self.group)      # nobody may still be writing into a table that goes away
+        for p in self._opened:
+            core().ntgb_peer_table_close(self.pb._h, p)
+        self._opened = []
+        dist.barrier(group=self.group)
+        if self._own:
+            core().ntgb_peer_table_free(self.pb._h, self._own)
+            self._own = None

@@ -221,7 +221,7 @@ def workload_config(cfg, spec, P, ngpus):
 
 
 # --------------------------------------------------------------------------- GPU arm
-def time_workload(torch, pb, spec, cfg, P, steps, warmup, dist=None, world=1, use_graph=False):
+def time_workload(torch, pb, spec, cfg, P, steps, warmup, dist=None, world=1, use_graph=False, peers=None):
     """-> dict(ms_per_step, kernel_ms, launches).  Ring of buffer sets larger than L2 when one
     set is not."""
     dev = torch.device("cuda", pb.device)
@@ -270,8 +270,8 @@ def time_workload(torch, pb, spec, cfg, P, steps, warmup, dist=None, world=1, us
     res2 = [torch.empty((P, 2), dtype=torch.float64, device=dev) for _ in range(NB)] if dist else None
     gath2 = [torch.empty((world * P, 2), dtype=torch.float64, device=dev) for _ in range(NB)] if dist else None
     if dist is not None:
-        args2 = [[pb.eval_args(x, dict(o, result=res2[b]), 2, 2, JAC_BAND, 0, stream.cuda_stream) for x, o in sets]
-                 for b in range(NB)]
+        args2 = [[pb.eval_args(x, dict(o, result=res2[b]), 2, 2, JAC_BAND, 0, stream.cuda_stream, peers=peers)
+                  for x, o in sets] for b in range(NB)]
     pending = [None] * NB
 
     def step(i, ev=None):
@@ -287,7 +287,7 @@ def time_workload(torch, pb, spec, cfg, P, steps, warmup, dist=None, world=1, us
             pb.launch(args[s])
         if ev is not None:
             ev[1].record()
-        if dist is not None:
+        if dist is not None and peers is None:
             pending[i % NB] = dist.all_gather_into_tensor(gath2[i % NB], res2[i % NB], async_op=True)
 
     def drain():
@@ -295,6 +295,8 @@ def time_workload(torch, pb, spec, cfg, P, steps, warmup, dist=None, world=1, us
             if pending[b] is not None:
                 pending[b].wait()
                 pending[b] = None
+        if peers is not None:
+            peers.fence()   # fused gather: the tables are complete once every rank's stream has drained
 
     for i in range(warmup):
         step(i)
@@ -313,9 +315,13 @@ def time_workload(torch, pb, spec, cfg, P, steps, warmup, dist=None, world=1, us
     if dist is not None:
         dist.barrier()
         want = res2[(steps - 1) % NB]
-        got = gath2[(steps - 1) % NB]
+        got = gath2[(steps - 1) % NB] if peers is None else peers.table()
         r0 = dist.get_rank()
         assert torch.equal(got[r0 * P:(r0 + 1) * P], want), "gathered table does not hold this rank's rows"
+        if peers is not None:
+            other = got[((r0 + 1) % world) * P:((r0 + 1) % world + 1) * P]
+            assert bool(torch.isfinite(other).all()) and float(other[:, 0].abs().sum()) > 0.0, \
+                "the neighbour's rows never arrived in this rank's gathered table"
     total_ms = e0.elapsed_time(e1)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
     chk = float((res2[0] if dist is not None else sets[0][1]["result"])[:, 0].sum().item())
@@ -468,6 +474,8 @@ def main():
     ap.add_argument("--variant", default=os.environ.get("NTG_BENCH_VARIANT", "fast"), choices=["exact", "fast"])
     ap.add_argument("--problems", type=int, default=0, help="override problems per GPU")
     ap.add_argument("--no-others", action="store_true", help="skip the other workloads / baselines")
+    ap.add_argument("--gather", default=os.environ.get("NTG_BENCH_GATHER", "fused"), choices=["fused", "nccl"],
+                    help="N > 1: how the 16 B/problem result table reaches every rank")
     ap.add_argument("--ref-step-seconds", type=float, default=1.0)
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
@@ -486,13 +494,15 @@ def main():
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
-        # The persistent evaluator fills every SM, so a co-running NCCL kernel can only start when
-        # evaluator CTAs retire and then holds back a few CTAs of the NEXT launch, which finish last.
-        # Measured per step (65 536 problems per GPU): N = 2, NCCL defaults 144 us; four SMs left free
-        # and the all-gather of the 16 B/problem table limited to four channels 139 us.  At N = 4
-        # and 8 the gathered table is 4 / 8 MB and needs NCCL's default channel count (138 / 149 us;
-        # four channels: 234 / 386 us), so the limit is applied to two ranks only.
-        if world == 2:
+        # --gather fused (default): the evaluator's epilogue stores each rank's (objective, violation)
+        # rows into EVERY rank's gathered table over NVLink (CUDA IPC peer tables, ntg_b200/shard.py::
+        # PeerGather); no collective kernel runs beside the persistent evaluator.
+        # --gather nccl: one asynchronous all_gather per step.  The persistent evaluator fills every
+        # SM, so the NCCL kernel can only start when evaluator CTAs retire and then holds back a few
+        # CTAs of the NEXT launch, which finish last (N = 2: 144 us per step; with four SMs left
+        # free and four NCCL channels 139 us; at N = 4 / 8 the 4 / 8 MB table needs NCCL's default
+        # channel count: 138 / 149 us).
+        if a.gather == "nccl" and world == 2:
             os.environ.setdefault("NTG_B200_SM_RESERVE", "4")
             os.environ.setdefault("NCCL_MAX_NCHANNELS", "4")
         import torch.distributed as dist
@@ -509,7 +519,19 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    r = time_workload(torch, pb, spec, a.workload, P, a.steps, a.warmup, dist, world)
+    peers = None
+    gather_how = "none"
+    if world > 1:
+        gather_how = "nccl all_gather_into_tensor, asynchronous, 4 rotating tables"
+        if a.gather == "fused":
+            try:
+                from ntg_b200.shard import PeerGather
+                peers = PeerGather(pb, world * P)
+                gather_how = "fused: peer stores from the evaluator's epilogue into every rank's table (CUDA IPC, NVLink)"
+            except Exception as e:  # no peer access between these GPUs: the collective still works
+                sys.stderr.write(f"bench: fused gather unavailable ({e}); using NCCL\n")
+                peers = None
+    r = time_workload(torch, pb, spec, a.workload, P, a.steps, a.warmup, dist, world, peers=peers)
     clocks = sampler.stop() if sampler else None
 
     ms = torch.tensor([r["ms_per_step"], r["kernel_ms"]], dtype=torch.float64, device="cuda")
@@ -554,6 +576,8 @@ def main():
         cfgd = workload_config(a.workload, spec, P, world)
         cfgd["variant"] = ("fast (FMA contraction, node-weight quadrature with 4 partial sums)" if fast else
                            "exact (-fmad=false, reference summation order, bit-identical to the CPU reference)")
+        if world > 1:
+            cfgd["gather"] = gather_how
         cfgd["l2"] = (f"inputs+outputs of one step = {r['footprint_mb']:.0f} MB over a ring of {r['nset']} "
                       f"buffer set(s), larger than the 126 MB L2")
         line = {

@@ -66,23 +66,47 @@ class PeerGather:
         if self.world > 8:
             raise ValueError("PeerGather: at most 8 ranks (NTGB_MAXPEERS)")
         self.row0 = shard_range(self.P_total, self.rank, self.world)[0]
+        # Every rank runs the SAME sequence of collectives whatever fails locally; success is agreed
+        # on at the end, so either all ranks get a PeerGather or all of them get the exception
+        # (a rank that silently fell back to a collective would deadlock the others).
+        self._torch = torch
+        self._own, self.tables, self._opened = None, [], []
+        ok, why = 1, ""
         own = C.c_void_p()
         handle = C.create_string_buffer(64)
-        _check(core().ntgb_peer_table_alloc(pb._h, self.P_total, C.byref(own), handle))
-        self._own = own.value
+        try:
+            _check(core().ntgb_peer_table_alloc(pb._h, self.P_total, C.byref(own), handle))
+            self._own = own.value
+        except Exception as e:
+            ok, why = 0, str(e)
         handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(handle.raw), group=group)
-        self.tables, self._opened = [], []
-        for r in range(self.world):
-            if r == self.rank:
-                self.tables.append(self._own)
-                continue
-            ptr = C.c_void_p()
-            _check(core().ntgb_peer_table_open(pb._h, handles[r], C.byref(ptr)))
-            self.tables.append(ptr.value)
-            self._opened.append(ptr.value)
-        dist.barrier(group=group)
-        self._torch = torch
+        dist.all_gather_object(handles, bytes(handle.raw) if ok else b"", group=group)
+        if ok and all(len(h) == 64 for h in handles):
+            try:
+                for r in range(self.world):
+                    if r == self.rank:
+                        self.tables.append(self._own)
+                        continue
+                    ptr = C.c_void_p()
+                    _check(core().ntgb_peer_table_open(pb._h, handles[r], C.byref(ptr)))
+                    self.tables.append(ptr.value)
+                    self._opened.append(ptr.value)
+            except Exception as e:
+                ok, why = 0, str(e)
+        else:
+            ok, why = 0, why or "another rank could not create its table"
+        flag = torch.tensor([ok], dtype=torch.int32, device=f"cuda:{pb.device}")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            for p in self._opened:
+                core().ntgb_peer_table_close(pb._h, p)
+            self._opened = []
+            dist.barrier(group=group)
+            if self._own:
+                core().ntgb_peer_table_free(pb._h, self._own)
+                self._own = None
+            raise RuntimeError("PeerGather: peer tables unavailable on at least one rank" + (f" ({why})" if why else ""))
+        return
 
     def table(self):
         """this rank's gathered table as a [P_total][2] float64 cuda tensor (a view, no copy)"""

@@ -64,12 +64,18 @@ __device__ __forceinline__ void st_stream(double *p, double v) { __stcs(p, v); }
 
 /* one entry (which = 0 objective, 1 violation) of problem p's result pair: the local table and, for
  * the fused multi-GPU gather, every rank's copy of the gathered table (peer stores over NVLink) */
+template <bool PEERS = true> /* PEERS = false: a specialisation that is known to run without peer tables */
 __device__ __forceinline__ void put_result(const ntgb_eval_args &A, size_t p, int which, double v)
 {
     if (A.result != nullptr) A.result[2 * p + which] = v;
-    for (int r = 0; r < A.npeers; r++) A.peer_result[r][2 * ((size_t)A.peer_row0 + p) + which] = v;
+    if constexpr (PEERS)
+        for (int r = 0; r < A.npeers; r++) A.peer_result[r][2 * ((size_t)A.peer_row0 + p) + which] = v;
 }
-__device__ __forceinline__ bool want_result(const ntgb_eval_args &A) { return A.result != nullptr || A.npeers > 0; }
+template <bool PEERS = true>
+__device__ __forceinline__ bool want_result(const ntgb_eval_args &A)
+{
+    return A.result != nullptr || (PEERS && A.npeers > 0);
+}
 
 /* a callback that writes *mode = -1 asks the solver to stop (reference src/ntg.c:369) */
 __device__ __forceinline__ void note_abort(const ntgb_eval_args &A, int mode)

@@ -305,7 +305,7 @@ __device__ __forceinline__ void cost_band(const ntgb_devtab &T, const double *Bt
 
 /* HOT = the solver's steady state, known at compile time: funobj mode 2 + funcon mode 2, Jacobian
  * in band layout, f / g / c / J all requested, Z not requested. */
-template <class PK, bool FULL, bool HOT = false>
+template <class PK, bool FULL, bool HOT = false, bool PEERS = true>
 __global__ void __launch_bounds__(256, 2)
 ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R, int segtot)
 {
@@ -732,9 +732,9 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                 } else {
                     const double y = (cI_s[plr] + gU) + cF_s[plr]; /* y = I + In + F, src/ntg.c:303,328 */
                     if (HOT || (obj_v && A.f != nullptr)) A.f[pb] = y;
-                    if (want_result(A)) {
-                        put_result(A, (size_t)pb, 0, obj_v ? y : 0.0);
-                        if (!con_v) put_result(A, (size_t)pb, 1, 0.0);
+                    if (want_result<PEERS>(A)) {
+                        put_result<PEERS>(A, (size_t)pb, 0, obj_v ? y : 0.0);
+                        if (!con_v) put_result<PEERS>(A, (size_t)pb, 1, 0.0);
                     }
                 }
             }
@@ -742,7 +742,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
         /* maximum constraint violation per problem: eight lanes per problem, then three shuffles.
          * Handed out from the END of the block: with fewer chains than threads these are warps that
          * have no chain to walk, so the two passes run side by side. */
-        if (con_v && want_result(A)) {
+        if (con_v && want_result<PEERS>(A)) {
             /* 8 lanes per problem when they fit beside the chains, else 4 (never fewer: the loop
              * below covers any size) */
             const int chain_threads = (nC + 1) * GR;
@@ -766,7 +766,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                 vm = fmax(vm, __shfl_xor_sync(0xffffffffu, vm, 1));
                 vm = fmax(vm, __shfl_xor_sync(0xffffffffu, vm, 2));
                 if (LV == 8) vm = fmax(vm, __shfl_xor_sync(0xffffffffu, vm, 4));
-                if (q < nv && part == 0 && p0 + plr < P) put_result(A, (size_t)(p0 + plr), 1, vm);
+                if (q < nv && part == 0 && p0 + plr < P) put_result<PEERS>(A, (size_t)(p0 + plr), 1, vm);
             }
         }
         /* the barrier at the top of the next iteration separates this phase B from the next phase A */
@@ -818,8 +818,12 @@ int launch_eval_small(const ntgb_launch *L)
     const ntgb_eval_args &a = L->args;
     const bool hot = a.mode_obj == 2 && a.mode_con == 2 && a.jac_layout == NTGB_JAC_BAND && a.J != nullptr &&
                      a.f != nullptr && a.g != nullptr && a.c != nullptr && a.Z == nullptr && T.ncnln > 0;
-    auto kern = full ? (hot ? ntg_eval_small_kernel<PK, true, true> : ntg_eval_small_kernel<PK, true, false>)
-                     : ntg_eval_small_kernel<PK, false, false>;
+    /* the steady-state kernel exists with and without the peer stores of the fused multi-GPU
+     * gather, so that the single-GPU instantiation carries none of their code */
+    auto kern = full ? (hot ? (a.npeers > 0 ? ntg_eval_small_kernel<PK, true, true, true>
+                                             : ntg_eval_small_kernel<PK, true, true, false>)
+                            : ntg_eval_small_kernel<PK, true, false, true>)
+                     : ntg_eval_small_kernel<PK, false, false, true>;
     int nb = 0;
     if (int rc = resident_blocks((const void *)kern, block, smem, L->max_smem_optin, &nb)) return rc;
     const int ntiles = (P + G * R - 1) / (G * R);

@@ -137,14 +137,16 @@ typedef struct ntgb_eval_args {
     /* Fused multi-GPU gather (optional; npeers = 0 turns it off).  Problems are sharded over the
      * GPUs of a node and the only thing the ranks exchange is the 16 B/problem (objective,
      * violation) table.  Instead of a collective after the kernel, the evaluator's epilogue stores
-     * each pair into EVERY rank's copy of the gathered table -- peer_result[r] is rank r's table
+     * each pair into EVERY rank's copy of the gathered table -- peer_result[r] (an array in device
+     * memory) is rank r's table
      * [total problems][2], mapped into this process (ntgb_peer_table_open: CUDA IPC, NVLink peer
      * stores); this rank's rows start at peer_row0.  No NCCL kernel competes with the persistent
      * evaluator for SMs.  A rank may read its table once every rank's stream has been
      * synchronised (a barrier), exactly when it could have waited for an asynchronous collective. */
-    int npeers;
+    int npeers;                   /* <= NTGB_MAXPEERS */
     int peer_row0;
-    double *peer_result[8]; /* NTGB_MAXPEERS */
+    double *const *peer_result;   /* DEVICE array [npeers] of table pointers (kept out of the kernel
+                                   * parameters: the evaluators are sensitive to their size) */
 } ntgb_eval_args;
 #define NTGB_MAXPEERS 8
 

@@ -76,7 +76,7 @@ class NtgbEvalArgs(C.Structure):
         ("abort_flag", C.c_void_p),
         ("npeers", C.c_int),
         ("peer_row0", C.c_int),
-        ("peer_result", C.c_void_p * 8),
+        ("peer_result", C.c_void_p),
     ]
 
 

@@ -1301,8 +1301,7 @@ int ntgb_eval(ntgb_problem *pb, const ntgb_eval_args *a)
         return fail(NTGB_EINVAL, "unknown jac_layout %d", a->jac_layout);
     if (a->npeers < 0 || a->npeers > NTGB_MAXPEERS || a->peer_row0 < 0)
         return fail(NTGB_EINVAL, "npeers = %d outside [0,%d] or negative peer_row0", a->npeers, NTGB_MAXPEERS);
-    for (int r = 0; r < a->npeers; r++)
-        if (!a->peer_result[r]) return fail(NTGB_EINVAL, "peer_result[%d] == NULL", r);
+    if (a->npeers > 0 && !a->peer_result) return fail(NTGB_EINVAL, "npeers = %d but peer_result == NULL", a->npeers);
     DeviceGuard dg(pb->device);
     if (!dg.ok) return fail(NTGB_ECUDA, "cannot select device %d", pb->device);
     ntgb_launch L;

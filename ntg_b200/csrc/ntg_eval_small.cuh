@@ -732,9 +732,14 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                 } else {
                     const double y = (cI_s[plr] + gU) + cF_s[plr]; /* y = I + In + F, src/ntg.c:303,328 */
                     if (HOT || (obj_v && A.f != nullptr)) A.f[pb] = y;
-                    if (want_result<PEERS>(A)) {
-                        put_result<PEERS>(A, (size_t)pb, 0, obj_v ? y : 0.0);
-                        if (!con_v) put_result<PEERS>(A, (size_t)pb, 1, 0.0);
+                    if constexpr (!PEERS) {
+                        if (A.result != nullptr) {
+                            A.result[2 * (size_t)pb] = obj_v ? y : 0.0;
+                            if (!con_v) A.result[2 * (size_t)pb + 1] = 0.0;
+                        }
+                    } else if (want_result(A)) {
+                        put_result(A, (size_t)pb, 0, obj_v ? y : 0.0);
+                        if (!con_v) put_result(A, (size_t)pb, 1, 0.0);
                     }
                 }
             }
@@ -742,7 +747,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
         /* maximum constraint violation per problem: eight lanes per problem, then three shuffles.
          * Handed out from the END of the block: with fewer chains than threads these are warps that
          * have no chain to walk, so the two passes run side by side. */
-        if (con_v && want_result<PEERS>(A)) {
+        if (con_v && (PEERS ? want_result(A) : A.result != nullptr)) {
             /* 8 lanes per problem when they fit beside the chains, else 4 (never fewer: the loop
              * below covers any size) */
             const int chain_threads = (nC + 1) * GR;
@@ -766,7 +771,10 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                 vm = fmax(vm, __shfl_xor_sync(0xffffffffu, vm, 1));
                 vm = fmax(vm, __shfl_xor_sync(0xffffffffu, vm, 2));
                 if (LV == 8) vm = fmax(vm, __shfl_xor_sync(0xffffffffu, vm, 4));
-                if (q < nv && part == 0 && p0 + plr < P) put_result<PEERS>(A, (size_t)(p0 + plr), 1, vm);
+                if (q < nv && part == 0 && p0 + plr < P) {
+                    if constexpr (!PEERS) A.result[2 * (size_t)(p0 + plr) + 1] = vm;
+                    else put_result(A, (size_t)(p0 + plr), 1, vm);
+                }
             }
         }
         /* the barrier at the top of the next iteration separates this phase B from the next phase A */

@@ -196,8 +196,7 @@ class Problem:
         if peers is not None:
             a.npeers = len(peers.tables)
             a.peer_row0 = peers.row0
-            for r, t in enumerate(peers.tables):
-                a.peer_result[r] = t
+            a.peer_result = peers.device_pointers()
         return a
 
     def launch(self, args: NtgbEvalArgs):

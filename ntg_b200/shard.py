@@ -108,6 +108,12 @@ class PeerGather:
             raise RuntimeError("PeerGather: peer tables unavailable on at least one rank" + (f" ({why})" if why else ""))
         return
 
+    def device_pointers(self) -> int:
+        """address of a device array holding the table pointers (ntgb_eval_args.peer_result)"""
+        if getattr(self, "_ptrs", None) is None:
+            self._ptrs = self._torch.tensor(self.tables, dtype=self._torch.int64, device=f"cuda:{self.pb.device}")
+        return self._ptrs.data_ptr()
+
     def table(self):
         """this rank's gathered table as a [P_total][2] float64 cuda tensor (a view, no copy)"""
         class _View:

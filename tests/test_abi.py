@@ -120,3 +120,33 @@ def test_dropin_host_helpers(built_libs):
     m[2][3] = 7.0
     assert m[0][11] == 7.0                                   # one contiguous block, row pointers
     lib.FreeDoubleMatrix(m)
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """the ctypes mirrors in ntg_b200/abi.py must have the C structs' size and field offsets
+    (gcc on include/ntg_b200.h says what those are)"""
+    import ctypes as C
+    import subprocess
+    from ntg_b200 import abi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pairs = {"ntgb_eval_args": abi.NtgbEvalArgs, "ntgb_solve_opts": abi.SolveOpts, "ntgb_nlp_opts": abi.NlpOpts,
+             "ntgb_dims": abi.NtgbDims, "ntgb_setup": abi.NtgbSetup, "ntgb_pack": abi.NtgbPack}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "ntg_b200.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines) + "\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    want = {}
+    for line in out.splitlines():
+        s, f, v = line.split()
+        want[(s, f)] = int(v)
+    for cname, cls in pairs.items():
+        assert C.sizeof(cls) == want[(cname, "size")], f"sizeof({cname})"
+        for fname, _ in cls._fields_:
+            assert getattr(cls, fname).offset == want[(cname, fname)], f"offsetof({cname}, {fname})"

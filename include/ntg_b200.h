@@ -95,6 +95,9 @@ typedef struct ntgb_dims {
     int ncnln;   /* nnlic + nnltc*nbps + nnlfc                           */
     int sorder;  /* S = sum_j order_j = band width of one Jacobian row   */
     int device;  /* CUDA device ordinal the tables live on               */
+    int band_tile; /* TB: breakpoints per tile of the band-compact Jacobian
+                    * layout (NTGB_JAC_BAND); TB = nbps unless the horizon
+                    * is split over a thread-block cluster                 */
 } ntgb_dims;
 
 /* Jacobian layouts for ntgb_eval */
@@ -104,12 +107,31 @@ typedef struct ntgb_dims {
  * zeroes the buffer once, exactly as the reference's one-time calloc does. */
 #define NTGB_JAC_DENSE 1
 /* Band-compact: per problem ncnln x S values.  Trajectory rows are stored
- * breakpoint-fastest: value of (row = nnlic + m*nbps + bp, band slot s) is at
- *   Jb[p*ncnln*S + nnlic*S + (m*S + s)*nbps + bp];
- * initial rows r at Jb[p*ncnln*S + r*S + s]; final rows r at
+ * breakpoint-fastest, in tiles of TB = ntgb_dims.band_tile breakpoints: with
+ * t = bp / TB, n_t = min(TB, nbps - t*TB) breakpoints in tile t, the value of
+ * (row = nnlic + m*nbps + bp, band slot s) is at
+ *   Jb[p*ncnln*S + nnlic*S + t*nnltc*S*TB + (m*S + s)*n_t + (bp - t*TB)];
+ * TB = nbps (one tile, Jb[... + (m*S + s)*nbps + bp]) for every horizon one CTA
+ * covers; long horizons that a thread-block cluster splits use one tile per
+ * CTA, so that each CTA streams ONE contiguous block of the problem's
+ * Jacobian (DRAM and copy-engine efficiency).
+ * ntgb_band_index() below is the index function.
+ * Initial rows r at Jb[p*ncnln*S + r*S + s]; final rows r at
  *   Jb[p*ncnln*S + (nnlic + nnltc*nbps)*S + r*S + s].
  * Band slot s = jk0[j] + k maps to column col0[row][j] + k (ntgb_pattern). */
 #define NTGB_JAC_BAND  2
+
+/* offset (in doubles, inside one problem's ncnln*S block) of band slot s of trajectory row
+ * (constraint m, breakpoint bp) in the NTGB_JAC_BAND layout */
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+static inline size_t ntgb_band_index(int nnlic, int nnltc, int S, int nbps, int band_tile, int m, int s, int bp)
+{
+    const int t = bp / band_tile;
+    const int nt = nbps - t * band_tile < band_tile ? nbps - t * band_tile : band_tile;
+    return (size_t)nnlic * S + (size_t)t * nnltc * S * band_tile + ((size_t)m * S + s) * nt + (size_t)(bp - t * band_tile);
+}
 
 /*
  * One batched evaluation.  All pointers are DEVICE pointers (or NULL to skip
@@ -315,6 +337,8 @@ typedef struct ntgb_pack {
     int maxderiv[8];
     int exact;  /* 1: reference operation order, no FMA contraction */
     int (*launch)(const struct ntgb_launch *);
+    int abi;    /* NTGB_KERNEL_ABI the pack was built against (ntg_kernel_args.h): a pack built
+                 * from an older header is refused at registration */
 } ntgb_pack;
 
 int ntgb_register_pack(const ntgb_pack *pack);

@@ -55,7 +55,7 @@ class NtgbSetup(C.Structure):
 
 class NtgbDims(C.Structure):
     _fields_ = [(n, C.c_int) for n in
-                ("nout", "nbps", "nC", "nz", "nZ", "nclin", "ncnln", "sorder", "device")]
+                ("nout", "nbps", "nC", "nz", "nZ", "nclin", "ncnln", "sorder", "device", "band_tile")]
 
 
 class NtgbEvalArgs(C.Structure):
@@ -102,6 +102,7 @@ class NtgbPack(C.Structure):
         ("maxderiv", C.c_int * 8),
         ("exact", C.c_int),
         ("launch", C.c_void_p),
+        ("abi", C.c_int),
     ]
 
 

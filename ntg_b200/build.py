@@ -236,7 +236,7 @@ def generate_wrapper(m: PackManifest, verbose: bool = False) -> str:
     for h in ("assert.h", "float.h", "math.h", "stdio.h", "stdlib.h", "string.h", "unistd.h"):
         L.append(f"#include <{h}>")
     L.append('#include "ntg.h"')
-    L.append('#include "ntg_eval_cluster.cuh"')
+    L.append('#include "ntg_eval_cluster_hot.cuh"')
     if m.c_compat:
         L.append("/* C-only idiom support: `double *p = calloc(...)` must parse as C++ */")
         L.append("namespace { struct ntg_voidp { void *p; template <class T> operator T *() const "
@@ -304,7 +304,7 @@ def build_pack(m: PackManifest, verbose: bool = False, force: bool = False, ptxa
     core = build_core(verbose)
     wrapper = generate_wrapper(m, verbose)
     so = pack_so(m.name)
-    deps = [wrapper, os.path.abspath(m.src), core, os.path.join(CSRC, "ntg_eval_kernel.cuh"), os.path.join(CSRC, "ntg_eval_small.cuh"), os.path.join(CSRC, "ntg_eval_cluster.cuh"),
+    deps = [wrapper, os.path.abspath(m.src), core, os.path.join(CSRC, "ntg_eval_kernel.cuh"), os.path.join(CSRC, "ntg_eval_small.cuh"), os.path.join(CSRC, "ntg_eval_cluster.cuh"), os.path.join(CSRC, "ntg_eval_cluster_hot.cuh"),
             os.path.join(CSRC, "ntg_kernel_args.h"), os.path.join(INCLUDE, "ntg_b200.h"),
             os.path.join(INCLUDE, "ntg.h")]
     if force or ptxas_v or _newer(so, deps):

@@ -632,7 +632,7 @@ __global__ void k_alm_grad(int P, ntgb_devtab T, int nclin, int n_li, const int 
                     if (k < 0 || k >= ord) continue;
                     for (int mm = 0; mm < T.nnltc; mm++)
                         acc += mun[T.nnlic + mm * nbps + bp] *
-                               Jp[(size_t)T.nnlic * S + ((size_t)mm * S + s0 + k) * nbps + bp];
+                               Jp[ntgb_band_index(T.nnlic, T.nnltc, S, nbps, T.band_tile, mm, s0 + k, bp)];
                 }
             }
             if (T.nnlfc > 0) {
@@ -803,11 +803,18 @@ void host_band_row(const ntgb_problem *pb, const double *dz, int bp, double *ban
 extern "C" {
 
 const char *ntgb_last_error(void) { return g_err.c_str(); }
-const char *ntgb_version(void) { return "ntg_b200 0.1 (sm_100a, kernel ABI 5)"; }
+#define NTGB_STR2(x) #x
+#define NTGB_STR(x) NTGB_STR2(x)
+const char *ntgb_version(void) { return "ntg_b200 0.2 (sm_100a, kernel ABI " NTGB_STR(NTGB_KERNEL_ABI) ")"; }
 
 int ntgb_register_pack(const ntgb_pack *pack)
 {
     if (!pack || !pack->launch || !pack->name) return fail(NTGB_EINVAL, "ntgb_register_pack: null pack");
+    /* ntgb_devtab / ntgb_eval_args travel BY VALUE into the pack's launcher: a pack built against
+     * another revision of ntg_kernel_args.h would reinterpret them silently */
+    if (pack->abi != NTGB_KERNEL_ABI)
+        return fail(NTGB_EINVAL, "callback pack '%s' was built for kernel ABI %d, this library is ABI %d: rebuild the pack "
+                    "(python -m ntg_b200.build)", pack->name, pack->abi, NTGB_KERNEL_ABI);
     std::lock_guard<std::mutex> lk(g_reg_mu);
     for (ntgb_pack &pk : registry())
         if (strcmp(pk.name, pack->name) == 0) {
@@ -1111,9 +1118,11 @@ int ntgb_create(ntgb_problem **out, const ntgb_setup *s, int device)
 
     /* quadrature plan for the cluster kernel (long horizons, one shared table) */
     T.plan_ptr = nullptr; T.plan = nullptr; T.plan_cl = 0; T.plan_bpc = 0; T.plan_cwin = 0; T.plan_n = 0;
+    T.band_tile = nbps; /* band-compact Jacobian: one tile unless a cluster splits the horizon */
     if (T.one_table && nbps > 256 && nbps <= 8 * 224) {
         int CL, bpc;
         ntgb_cluster_geometry(nbps, &CL, &bpc);
+        T.band_tile = bpc; /* one tile per CTA of the cluster: each CTA streams one contiguous block */
         std::vector<int> ptr(T.ncoef[0] + 1, 0);
         std::vector<int2> ent;
         for (int cl = 0; cl < T.ncoef[0]; cl++) {
@@ -1225,6 +1234,7 @@ int ntgb_create(ntgb_problem **out, const ntgb_setup *s, int device)
     }
     CUDA_TRY(cudaDeviceSynchronize());
     cleanup.p = nullptr;
+    pb->dims.band_tile = T.band_tile;
     *out = pb;
     return 0;
 }

@@ -335,11 +335,14 @@ ntg_eval_cluster_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL, int
                         }
                         if (wantJ) {
                             if (A.jac_layout == NTGB_JAC_BAND) {
+                                /* tiled band layout, one tile per CTA (include/ntg_b200.h): this CTA's
+                                 * rows are cnt = min(bpc, nbps - bp0) long and contiguous */
+                                const int cnt = nbps - bp0 < bpc ? nbps - bp0 : bpc;
                                 double *ptr = A.J + (size_t)p * T.ncnln * S + (size_t)T.nnlic * S +
-                                              (size_t)m * S * nbps + bp;
+                                              (size_t)rank * T.nnltc * S * bpc + (size_t)m * S * cnt + lbp;
                                 band_from_regs<PK, FULL, true>(T, Bt, dfc[m], [&](auto, auto, double v) {
                                     st_stream(ptr, v);
-                                    ptr += nbps;
+                                    ptr += cnt;
                                 });
                             } else {
                                 double *Jp = A.J + (size_t)p * T.ncnln * nC;
@@ -535,7 +538,7 @@ int launch_eval_cluster(const ntgb_launch *L)
         if (nbps > 8 * 224) return -1001;
         int bpc;
         ntgb_cluster_geometry(nbps, &CL, &bpc);
-        if (T.plan == nullptr || T.plan_cl != CL || T.plan_bpc != bpc) return -1001;
+        if (T.plan == nullptr || T.plan_cl != CL || T.plan_bpc != bpc || T.band_tile != bpc) return -1001;
         const int block = (bpc + 31) / 32 * 32 + 32; /* + one service warp (scalar cost of the previous problem) */
         if (block > 256) return -1001;
         bool full = true;
@@ -569,29 +572,6 @@ int launch_eval_cluster(const ntgb_launch *L)
         cfg.numAttrs = 1;
         return (int)cudaLaunchKernelEx(&cfg, kern, T, L->args, CL, bpc, T.plan_cwin, plan_smem);
     }
-}
-
-/* dispatcher used by NTGB_DEFINE_PACK: K1s (small, register tables) -> K1c (long horizon, one
- * shared table, thread-block clusters) -> K1 (general) */
-template <class PK>
-int launch_dispatch(const ntgb_launch *L)
-{
-    /* NTG_B200_KERNEL=general forces K1 (A/B measurements, tests of both kernels) */
-    const char *env = getenv("NTG_B200_KERNEL");
-    const bool force_general = env != nullptr && strcmp(env, "general") == 0;
-    if (!force_general) {
-        if constexpr (pk_tab_doubles<PK>() <= 64) {
-            if (small_shape_ok<PK>(L->tab)) {
-                const int rc = launch_eval_small<PK>(L);
-                if (rc != -1001) return rc;
-            }
-        }
-        if (L->tab.nbps > 256) {
-            const int rc = launch_eval_cluster<PK>(L);
-            if (rc != -1001) return rc;
-        }
-    }
-    return launch_eval<PK>(L);
 }
 
 } /* namespace ntgb */

@@ -34,6 +34,7 @@
 #define NTG_EVAL_KERNEL_CUH_
 
 #include <cuda_runtime.h>
+#include <cstdio>
 #include <type_traits>
 
 #include "ntg_kernel_args.h"
@@ -133,8 +134,8 @@ __device__ __forceinline__ void emit_jac_rows(const ntgb_devtab &T, const ntgb_e
                     for (int l = 0; l < MD; l++) acc = acc + dfc[m][IZ + l] * b[l];
                     if (A.jac_layout == NTGB_JAC_BAND) {
                         size_t idx;
-                        if (KIND == 1)
-                            idx = pbase_band + (size_t)row_base * T.S + ((size_t)m * T.S + s0 + k) * nbps + bp;
+                        if (KIND == 1) /* tiled, breakpoint-fastest (include/ntg_b200.h); row_base = nnlic */
+                            idx = pbase_band + ntgb_band_index(row_base, T.nnltc, T.S, nbps, T.band_tile, m, s0 + k, bp);
                         else
                             idx = pbase_band + (size_t)(row_base + m) * T.S + s0 + k;
                         st_stream(A.J + idx, acc);
@@ -581,7 +582,9 @@ int launch_eval(const ntgb_launch *L)
             pk.max_nnlic = TRAITS::kNnlic; pk.max_nnltc = TRAITS::kNnltc; pk.max_nnlfc = TRAITS::kNnlfc;  \
             pk.exact = EXACT;                                                                   \
             pk.launch = ntgb_pack_launch_##NAME;                                                \
-            ntgb_register_pack(&pk);                                                            \
+            pk.abi = NTGB_KERNEL_ABI;                                                           \
+            if (ntgb_register_pack(&pk) != 0)                                                   \
+                fprintf(stderr, "ntg_b200: pack '%s' not registered: %s\n", #NAME, ntgb_last_error()); \
         }                                                                                       \
     } ntgb_pack_registrar_instance_##NAME;                                                      \
     }

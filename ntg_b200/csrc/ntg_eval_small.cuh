@@ -786,7 +786,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
 template <class PK>
 __host__ inline bool small_shape_ok(const ntgb_devtab &T)
 {
-    return pk_tab_doubles<PK>() <= 64 && T.nbps <= 256;
+    return pk_tab_doubles<PK>() <= 64 && T.nbps <= 256 && T.band_tile == T.nbps; /* band rows of nbps values */
 }
 
 template <class PK>

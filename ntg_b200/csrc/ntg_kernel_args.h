@@ -2,7 +2,8 @@
  * ntg_kernel_args.h -- the POD block handed from the core library
  * (ntg_core.cu) to a callback pack's launcher (ntg_eval_kernel.cuh).
  * Internal: not part of the public ABI, but both sides are built from this
- * header, and NTGB_KERNEL_ABI is checked at pack registration.
+ * header; ntgb_register_pack() refuses a pack whose NTGB_KERNEL_ABI differs
+ * and every launcher checks ntgb_launch.abi again.
  */
 #ifndef NTG_KERNEL_ARGS_H_
 #define NTG_KERNEL_ARGS_H_
@@ -11,7 +12,7 @@
 
 #include <vector_types.h>
 
-#define NTGB_KERNEL_ABI 10
+#define NTGB_KERNEL_ABI 11
 #define NTGB_MAXOUT 8      /* outputs per problem the device tables can describe */
 #define NTGB_MAXORDER 20   /* PGS bsplvb work arrays: jmax = 20   */
 #define NTGB_MAXNLB 16     /* nonlinear bounds carried by value in the kernel params */
@@ -26,6 +27,7 @@ typedef struct ntgb_devtab {
      * <=> z[j][d] is computed there.  cls = (bp==0) | (bp==nbps-1)<<1.
      * (updateZ only fills listed variables, reference src/colloc.c:344-367) */
     unsigned avmask[4][NTGB_MAXOUT];
+    int band_tile;                  /* breakpoints per tile of the band-compact Jacobian (ntg_b200.h) */
     const double *Bt[NTGB_MAXOUT];  /* [(k*maxderiv+d)*nbps + bp]  breakpoint-fastest      */
     const double *Bn[NTGB_MAXOUT];  /* [(bp*order+k)*maxderiv + d] reference block layout  */
     const int *off[NTGB_MAXOUT];    /* [bp] block offset (reference src/colloc.c:108)      */

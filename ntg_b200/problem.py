@@ -71,7 +71,7 @@ def load_pack(name: str) -> C.CDLL:
     """dlopen a callback pack; its static initialiser registers it with the core."""
     core()
     if name not in _packs:
-        path = os.path.join(_LIBDIR, f"libntgpack_{name}.so")
+        path = os.path.join(os.environ.get("NTG_B200_PACK_DIR", _LIBDIR), f"libntgpack_{name}.so")
         if not os.path.exists(path):
             raise NtgError(f"callback pack {path} is missing: build it with `python -m ntg_b200.build`")
         _packs[name] = C.CDLL(path)  # RTLD_LOCAL: exact/fast variants define the same symbols
@@ -252,19 +252,22 @@ class Problem:
 
     # ---- band <-> (row, col, value) ----
     def band_to_rows(self, Jband: np.ndarray) -> np.ndarray:
-        """device band layout [P][ncnln*S] (trajectory rows breakpoint-fastest) ->
-        row-major [P][ncnln][S], the layout the CPU oracles report"""
+        """device band layout [P][ncnln*S] (trajectory rows breakpoint-fastest, in tiles of
+        dims.band_tile breakpoints: include/ntg_b200.h, NTGB_JAC_BAND) -> row-major [P][ncnln][S],
+        the layout the CPU oracles report"""
         s, d = self.spec, self.dims
-        P, S, nb = Jband.shape[0], d.sorder, s.nbps
+        P, S, nb, TB = Jband.shape[0], d.sorder, s.nbps, d.band_tile
         out = np.empty((P, d.ncnln, S))
         pos = 0
         n = s.nnlic * S
         out[:, :s.nnlic, :] = Jband[:, pos:pos + n].reshape(P, s.nnlic, S)
         pos += n
-        n = s.nnltc * S * nb
-        out[:, s.nnlic:s.nnlic + s.nnltc * nb, :] = (
-            Jband[:, pos:pos + n].reshape(P, s.nnltc, S, nb).transpose(0, 1, 3, 2).reshape(P, s.nnltc * nb, S))
-        pos += n
+        traj = out[:, s.nnlic:s.nnlic + s.nnltc * nb, :].reshape(P, s.nnltc, nb, S)
+        for b0 in range(0, nb, TB):          # tile = breakpoints [b0, b0 + nt): values [m][slot][bp - b0]
+            nt = min(TB, nb - b0)
+            n = s.nnltc * S * nt
+            traj[:, :, b0:b0 + nt, :] = Jband[:, pos:pos + n].reshape(P, s.nnltc, S, nt).transpose(0, 1, 3, 2)
+            pos += n
         n = s.nnlfc * S
         out[:, s.nnlic + s.nnltc * nb:, :] = Jband[:, pos:pos + n].reshape(P, s.nnlfc, S)
         return out

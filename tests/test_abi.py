@@ -18,6 +18,7 @@ def declared_functions(header):
     txt = open(os.path.join(INCLUDE, header)).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     txt = re.sub(r"^\s*#.*$", "", txt, flags=re.M)          # preprocessor lines
+    txt = re.sub(r"(__host__ __device__\s*)?static inline[^{;]*\{.*?^\}", "", txt, flags=re.S | re.M)  # inline helpers: not exported
     txt = re.sub(r"typedef[^;]*\(\*[^;]*;", "", txt)       # function-pointer typedefs
     txt = re.sub(r"\w+ \(\*\w+\)\([^)]*\)", "void *cb", txt)  # callback parameters / members
     return sorted(set(re.findall(r"\b(\w+)\s*\([^;{]*\)\s*;", txt)) - {"defined"})

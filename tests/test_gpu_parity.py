@@ -176,6 +176,40 @@ def test_cluster_kernel_long_horizons(torch_cuda, port, ninterv, P, fast):
             pb.close()
 
 
+@pytest.mark.parametrize("ninterv,nbps,P", [(200, None, 3), (200, None, 150), (150, None, 75), (150, 300, 7), (300, None, 40),
+                                            (300, 890, 5), (640, None, 20), (101, 257, 9)])
+@pytest.mark.parametrize("fast", [False, True], ids=["exact", "fast"])
+def test_cluster_hot_kernel(torch_cuda, port, ninterv, nbps, P, fast, monkeypatch):
+    """K1c/H, the steady-state cluster kernel (mode 2/2, band layout, no Z): Jacobian rows staged in
+    shared memory and drained by cp.async.bulk.  Odd and even nbps (rows that start on odd and even
+    elements), clusters of 2 / 4 / 8, CTAs with a ragged last warp, batches below, at and above the
+    number of clusters, every ring depth the launcher may choose; and the same launch on the
+    general-mode cluster kernel must agree bit for bit."""
+    torch = torch_cuda
+    spec = configs.syn6(ninterv, nbps=nbps, name=f"syn6_{ninterv}_{nbps}")
+    X = configs.coefficients("cfg5", P, spec, seed=ninterv)
+    o = port.eval(spec, X, dense=False, band=True)
+    cmp = assert_bitexact if not fast else assert_close
+    res = {}
+    for stages in ("2", "3", "6"):
+        monkeypatch.setenv("NTG_B200_HOT_STAGES", stages)
+        pb, r = gpu_eval(torch, spec, X, fast)
+        for k in ("f", "g", "c", "Jband"):
+            cmp(r[k], o[k], f"syn6/{ninterv}/{nbps} stages={stages}: {k}")
+        assert_close(r["result"][:, 1], violation(spec, o["c"]), "violation")
+        assert np.array_equal(r["result"][:, 0], r["f"])
+        res[stages] = r
+        pb.close()
+    monkeypatch.delenv("NTG_B200_HOT_STAGES")
+    monkeypatch.setenv("NTG_B200_KERNEL", "cluster")
+    pb, r = gpu_eval(torch, spec, X, fast)
+    pb.close()
+    for k in ("f", "c", "J", "result") + (() if fast else ("g",)):
+        assert np.array_equal(r[k], res["6"][k]), f"K1c/H and K1c disagree in {k}"
+    if fast:
+        assert_close(r["g"], res["6"]["g"], "g")
+
+
 def test_cluster_kernel_dense_layout(torch_cuda, port):
     spec = configs.syn6(140, name="syn6_140")
     X = configs.coefficients("cfg5", 2, spec, seed=3)
@@ -362,7 +396,8 @@ def test_callback_abort_request(torch_cuda):
     pb.close()
 
 
-@pytest.mark.parametrize("case", ["k1s_endpoint", "k1s_kincar64", "k1_endpoint", "k1_syn6", "k1c_301", "k1c_601"])
+@pytest.mark.parametrize("case", ["k1s_endpoint", "k1s_kincar64", "k1_endpoint", "k1_syn6", "k1c_301", "k1c_601", "k1ch_301",
+                                  "k1ch_300", "k1ch_601"])
 @pytest.mark.parametrize("jac", [JAC_BAND, JAC_DENSE], ids=["band", "dense"])
 def test_no_out_of_bounds_writes(torch_cuda, case, jac, monkeypatch):
     """compute-sanitizer is closed on this pool: every output lives inside a larger buffer of
@@ -373,7 +408,12 @@ def test_no_out_of_bounds_writes(torch_cuda, case, jac, monkeypatch):
     from ntg_b200.abi import NtgbEvalArgs
     spec, P = {"k1s_endpoint": (configs.endpoint(), 7), "k1s_kincar64": (configs.kincar(64), 9),
                "k1_endpoint": (configs.endpoint(), 7), "k1_syn6": (configs.syn6(12, name="s12"), 3),
-               "k1c_301": (configs.syn6(150, name="s150"), 3), "k1c_601": (configs.syn6(300, name="s300"), 2)}[case]
+               "k1c_301": (configs.syn6(150, name="s150"), 3), "k1c_601": (configs.syn6(300, name="s300"), 2),
+               "k1ch_301": (configs.syn6(150, name="s150"), 3), "k1ch_300": (configs.syn6(150, nbps=300, name="s150e"), 4),
+               "k1ch_601": (configs.syn6(300, name="s300"), 2)}[case]
+    hot = case.startswith("k1ch")   # no Z requested: the steady-state kernels
+    if hot and jac == JAC_DENSE:
+        pytest.skip("steady-state kernels are band-layout only")
     if case == "k1_endpoint":
         monkeypatch.setenv("NTG_B200_KERNEL", "general")
     if jac == JAC_DENSE and spec.ncnln * spec.nC * P > 4e7:
@@ -388,7 +428,8 @@ def test_no_out_of_bounds_writes(torch_cuda, case, jac, monkeypatch):
     a = NtgbEvalArgs()
     a.P, a.C, a.mode_obj, a.mode_con, a.nstate = P, X.data_ptr(), 2, 2, 0
     for k in ("f", "g", "c", "J", "Z", "result"):
-        setattr(a, k, big[k].data_ptr() + PAD * 8)
+        if not (hot and k == "Z"):
+            setattr(a, k, big[k].data_ptr() + PAD * 8)
     a.jac_layout = jac
     a.stream = torch.cuda.current_stream().cuda_stream
     pb.launch(a)
@@ -396,7 +437,9 @@ def test_no_out_of_bounds_writes(torch_cuda, case, jac, monkeypatch):
     for k, n in sizes.items():
         b = big[k].cpu().numpy()
         assert np.all(b[:PAD] == S) and np.all(b[PAD + n:] == S), f"{case}: wrote outside {k}"
-        if k != "J" or jac == JAC_BAND:
+        if hot and k == "Z":
+            assert np.all(b == S), "Z was not requested"
+        elif k != "J" or jac == JAC_BAND:
             assert not np.any(b[PAD:PAD + n] == S), f"{case}: {k} not fully written"
     pb.close()
 

@@ -1116,50 +1116,107 @@ int ntgb_create(ntgb_problem **out, const ntgb_setup *s, int device)
             pb->ninterv[j] != pb->ninterv[0] || pb->knots[j] != pb->knots[0])
             T.one_table = 0;
 
-    /* quadrature plan for the cluster kernel (long horizons, one shared table) */
+    /* quadrature plans for the cluster kernels (long horizons, one shared table) */
     T.plan_ptr = nullptr; T.plan = nullptr; T.plan_cl = 0; T.plan_bpc = 0; T.plan_cwin = 0; T.plan_n = 0;
     T.band_tile = nbps; /* band-compact Jacobian: one tile unless a cluster splits the horizon */
+    T.plan_halo = -1;
+    T.plan_share = 0;
     if (T.one_table && nbps > 256 && nbps <= 8 * 224) {
-        int CL, bpc;
-        ntgb_cluster_geometry(nbps, &CL, &bpc);
-        T.band_tile = bpc; /* one tile per CTA of the cluster: each CTA streams one contiguous block */
-        std::vector<int> ptr(T.ncoef[0] + 1, 0);
-        std::vector<int2> ent;
-        for (int cl = 0; cl < T.ncoef[0]; cl++) {
-            int lo = nbps, hi = -1;
+        const int ncoef0 = T.ncoef[0], ord0 = T.order[0];
+        /* support of every local column, in breakpoints */
+        std::vector<int> clo(ncoef0, nbps), chi(ncoef0, -1);
+        int hsup = 0;
+        for (int cl = 0; cl < ncoef0; cl++) {
             for (int bp = 0; bp < nbps; bp++) {
                 const int k = cl - pb->hoff[bp];
-                if (k >= 0 && k < T.order[0]) { if (bp < lo) lo = bp; if (bp > hi) hi = bp; }
+                if (k >= 0 && k < ord0) { if (bp < clo[cl]) clo[cl] = bp; if (bp > chi[cl]) chi[cl] = bp; }
             }
+            if (chi[cl] >= 0 && chi[cl] - clo[cl] > hsup) hsup = chi[cl] - clo[cl];
+        }
+        /* room for the halo breakpoints of K1c/H among the 224 breakpoint-threads of a CTA */
+        int per_cta = 224 - 2 * hsup;
+        if (per_cta < 64) per_cta = 224;
+        int CL, bpc;
+        ntgb_cluster_geometry(nbps, per_cta, &CL, &bpc);
+        if ((long long)CL * bpc < nbps || bpc > 224) return fail(NTGB_ELIMIT, "internal: cluster geometry");
+        T.band_tile = bpc; /* one tile per CTA of the cluster: each CTA streams one contiguous block */
+        std::vector<int> ptr(ncoef0 + 1, 0);
+        std::vector<int2> ent;
+        for (int cl = 0; cl < ncoef0; cl++) {
             ptr[cl] = (int)ent.size();
-            if (hi >= 0) {
-                const int i0 = lo > 0 ? lo - 1 : 0;
-                const int nend = (hi < nbps - 2 ? hi : nbps - 2) + 1;
+            if (chi[cl] >= 0) {
+                const int i0 = clo[cl] > 0 ? clo[cl] - 1 : 0;
+                const int nend = (chi[cl] < nbps - 2 ? chi[cl] : nbps - 2) + 1;
                 for (int n = i0; n <= nend; n++) {
                     const int k = cl - pb->hoff[n];
                     const int r = n / bpc, li = n - r * bpc;
-                    const int o24 = (k >= 0 && k < T.order[0]) ? k * bpc + li : 0xffffff;
+                    const int o24 = (k >= 0 && k < ord0) ? k * bpc + li : 0xffffff;
                     ent.push_back(make_int2(n, (r << 24) | o24));
                 }
             }
         }
-        ptr[T.ncoef[0]] = (int)ent.size();
+        ptr[ncoef0] = (int)ent.size();
         if (ent.empty()) ent.push_back(make_int2(0, 0));
+        const int plan_n = (int)ent.size();
+        /* second plan (K1c/H, ntg_kernel_args.h): column cl belongs to rank own(cl) alone */
+        auto own = [&](int cl) {
+            int r = 0;
+            while (r + 1 < CL && cl >= (int)(((long long)ncoef0 * (r + 1)) / CL)) r++;
+            return r;
+        };
+        int halo = 0;
+        for (int cl = 0; cl < ncoef0; cl++)
+            if (chi[cl] >= 0) {
+                const int r = own(cl), first = r * bpc, last = (first + bpc < nbps ? first + bpc : nbps) - 1;
+                if (first - clo[cl] > halo) halo = first - clo[cl];
+                if (chi[cl] - last > halo) halo = chi[cl] - last;
+            }
+        bool hot_ok = bpc + 2 * halo <= 224 && ncoef0 / CL >= ord0;
+        const bool fast_pack = pb->pack_copy.exact == 0;
+        std::vector<int> hptr(ncoef0 + 1, 0);
+        std::vector<int2> hent;
+        if (hot_ok) {
+            const int pitch = bpc + 2 * halo;
+            for (int cl = 0; cl < ncoef0; cl++) {
+                hptr[cl] = plan_n + (int)hent.size();
+                if (chi[cl] < 0) continue;
+                const int r = own(cl);
+                const int i0 = clo[cl] > 0 ? clo[cl] - 1 : 0;
+                const int nend = (chi[cl] < nbps - 2 ? chi[cl] : nbps - 2) + 1;
+                for (int n = i0; n <= nend; n++) {
+                    const int k = cl - pb->hoff[n];
+                    const bool in = k >= 0 && k < ord0;
+                    if (!in && fast_pack) continue; /* node-weight quadrature: in-band terms only */
+                    hent.push_back(make_int2(n, in ? k * pitch + (n - r * bpc + halo) : -1));
+                }
+            }
+            hptr[ncoef0] = plan_n + (int)hent.size();
+            T.plan_share = 0;
+            for (int r = 0; r < CL; r++) {
+                const int a = (int)(((long long)ncoef0 * r) / CL), b = (int)(((long long)ncoef0 * (r + 1)) / CL);
+                if (hptr[b] - hptr[a] > T.plan_share) T.plan_share = hptr[b] - hptr[a];
+            }
+            ptr.insert(ptr.end(), hptr.begin(), hptr.end());
+            ent.insert(ent.end(), hent.begin(), hent.end());
+            T.plan_halo = halo;
+        }
         int *dptr = nullptr; int2 *dent = nullptr;
         if ((rc = dev_upload(pb, &dptr, ptr.data(), ptr.size()))) return rc;
         if ((rc = dev_upload(pb, &dent, ent.data(), ent.size()))) return rc;
         T.plan_ptr = dptr; T.plan = dent; T.plan_cl = CL; T.plan_bpc = bpc;
+        const int hw = T.plan_halo > 0 ? T.plan_halo : 0;
         int wmax = 0;
-        for (int r = 0; r < CL; r++) {
+        for (int r = 0; r < CL; r++) { /* coefficient window of rank r's breakpoints (+ halo) */
             int lo = 0x7fffffff, hi = -1;
-            for (int bp = r * bpc; bp < (r + 1) * bpc && bp < nbps; bp++) {
+            for (int bp = r * bpc - hw; bp < (r + 1) * bpc + hw; bp++) {
+                if (bp < 0 || bp >= nbps) continue;
                 lo = pb->hoff[bp] < lo ? pb->hoff[bp] : lo;
                 hi = pb->hoff[bp] > hi ? pb->hoff[bp] : hi;
             }
-            if (hi >= 0 && hi + T.order[0] - lo > wmax) wmax = hi + T.order[0] - lo;
+            if (hi >= 0 && hi + ord0 - lo > wmax) wmax = hi + ord0 - lo;
         }
         T.plan_cwin = wmax * nout;
-        T.plan_n = (int)ent.size();
+        T.plan_n = plan_n;
     }
 
     /* Jacobian row pattern (reference src/colloc.c:243-316) */

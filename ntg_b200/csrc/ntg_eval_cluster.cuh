@@ -534,11 +534,9 @@ int launch_eval_cluster(const ntgb_launch *L)
         const ntgb_devtab &T = L->tab;
         const int nbps = T.nbps, P = L->args.P;
         if (!devtab_one_table(T)) return -1001;
-        int CL;
-        if (nbps > 8 * 224) return -1001;
-        int bpc;
-        ntgb_cluster_geometry(nbps, &CL, &bpc);
-        if (T.plan == nullptr || T.plan_cl != CL || T.plan_bpc != bpc || T.band_tile != bpc) return -1001;
+        /* cluster geometry and plan were decided when the tables were built (ntg_core.cu) */
+        const int CL = T.plan_cl, bpc = T.plan_bpc;
+        if (T.plan == nullptr || CL < 2 || T.band_tile != bpc) return -1001;
         const int block = (bpc + 31) / 32 * 32 + 32; /* + one service warp (scalar cost of the previous problem) */
         if (block > 256) return -1001;
         bool full = true;

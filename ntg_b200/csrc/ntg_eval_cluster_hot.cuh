@@ -106,25 +106,59 @@ __device__ __forceinline__ void sts_f64(unsigned addr, double v)
     asm volatile("st.shared.f64 [%0+%1], %2;\n" ::"r"(addr), "n"(BYTE_OFF), "d"(v));
 }
 
+/* mbarrier in ANOTHER CTA of the cluster */
+__device__ __forceinline__ unsigned map_to_rank(unsigned local_smem_addr, int rank)
+{
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+    return r;
+}
+/* publishes this thread's earlier writes (incl. stores into the target CTA's shared memory) cluster-wide */
+__device__ __forceinline__ void mbar_arrive_remote_release(unsigned remote_bar)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(remote_bar) : "memory");
+}
+/* nothing to publish ("I am done reading"): no fence */
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(unsigned remote_bar)
+{
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(unsigned bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads)
+{
+    asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 struct ClusterHotSmem {
-    int bpc, nbps, S, cwin, ord, nst;
-    int plan_n, plan_cols; /* quadrature plan kept in shared memory (0 = left in global memory) */
+    int bpc, nbps, S, cwin, ord, nst, halo, cl;
+    int plan_n, plan_cols; /* this CTA's share of the quadrature plan in shared memory (0 = left in global memory) */
     __host__ __device__ static size_t even(size_t n) { return (n + 1) & ~(size_t)1; }
     /* one stage: [ord][cnt] values (cnt <= bpc) behind an optional alignment slot, even size */
     __host__ __device__ size_t stage_doubles() const { return even((size_t)ord * bpc + 1); }
+    __host__ __device__ int dpitch() const { return bpc + 2 * halo; }                                 /* a row of D: halo | own | halo */
     __host__ __device__ size_t ring_off() const { return 0; }                                        /* [nst][stage], 16-byte aligned */
-    __host__ __device__ size_t D_off() const { return (size_t)nst * stage_doubles(); }                /* [S][bpc]    */
-    __host__ __device__ size_t DI_off() const { return D_off() + (size_t)S * bpc; }                   /* [S]         */
+    __host__ __device__ size_t D_off() const { return (size_t)nst * stage_doubles(); }                /* [S][dpitch] */
+    __host__ __device__ size_t DI_off() const { return D_off() + (size_t)S * dpitch(); }              /* [S]         */
     __host__ __device__ size_t DF_off() const { return DI_off() + S; }                                /* [S]         */
-    __host__ __device__ size_t viol_off() const { return DF_off() + S; }                              /* u64 [2]     */
-    __host__ __device__ size_t sc_off() const { return viol_off() + 2; }                              /* cI, cF (rank 0) */
-    __host__ __device__ size_t fall_off() const { return sc_off() + 2; }                              /* [nbps] (rank 0) */
-    __host__ __device__ size_t t_off() const { return fall_off() + nbps; }                            /* [nbps] (rank 0) */
+    __host__ __device__ size_t viol_off() const { return DF_off() + S; }                              /* u64 [2] this CTA's maximum */
+    __host__ __device__ size_t violx_off() const { return viol_off() + 2; }                           /* u64 [2][cl] (rank 0): every rank's */
+    __host__ __device__ size_t sc_off() const { return violx_off() + 2 * (size_t)cl; }                /* [2][2] cI, cF (rank 0) */
+    __host__ __device__ size_t fall_off() const { return sc_off() + 4; }                              /* rank 0: [2][nbps]; others: [2][bpc] own integrand */
+    __host__ __device__ size_t t_off() const { return fall_off() + 2 * (size_t)nbps; }                /* [nbps] (rank 0) */
     __host__ __device__ size_t dt_off() const { return t_off() + nbps; }                              /* [nbps]      */
     __host__ __device__ size_t wf_off() const { return dt_off() + nbps; }                             /* [nbps] node weights (fast variant) */
     __host__ __device__ size_t C_off() const { return wf_off() + nbps; }                              /* [cwin]      */
-    __host__ __device__ size_t bar_off() const { return C_off() + cwin; }                             /* u64 [2*nst] full, empty */
-    __host__ __device__ size_t plan_off() const { return bar_off() + 2 * (size_t)nst; }               /* int2 [plan_n], int [plan_cols+1] */
+    __host__ __device__ size_t bar_off() const { return C_off() + cwin; }                             /* u64 [2*nst + 4] full, empty, ready[2], free[2] */
+    __host__ __device__ size_t plan_off() const { return bar_off() + 2 * (size_t)nst + 4; }           /* int2 [plan_n], int [plan_cols+1] */
     __host__ __device__ size_t bytes() const { return (plan_off() + plan_n) * 8 + (size_t)(plan_cols + 2) * 4 + 16; }
 };
 
@@ -147,7 +181,7 @@ __device__ __forceinline__ void band_one_output(const double *Bt, const double *
 
 template <class PK, bool PEERS>
 __global__ void __launch_bounds__(256, 1)
-ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL, int bpc, int cwin, int plan_smem, int NST)
+ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int cwin, int plan_smem, int NST, int plan_share)
 {
     constexpr int NOUT = PK::kNout;
     constexpr int NZ = pk_nz<PK>();
@@ -158,25 +192,31 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL,
     extern __shared__ __align__(16) double smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
-    const ClusterHotSmem L{bpc, T.nbps, T.S, cwin, ORD, NST, plan_smem ? T.plan_n : 0, plan_smem ? T.ncoef[0] : 0};
-    const int nbps = T.nbps, nC = T.nC, P = A.P, S = T.S;
+    const int CL = T.plan_cl, bpc = T.plan_bpc, H = T.plan_halo;
+    const int nbps = T.nbps, nC = T.nC, P = A.P, S = T.S, ncoef0 = T.ncoef[0];
+    /* quadrature columns of this CTA: a contiguous range, so that the chains stay inside its own D */
+    const int c_lo = (int)(((long long)ncoef0 * rank) / CL), c_hi = (int)(((long long)ncoef0 * (rank + 1)) / CL);
+    const ClusterHotSmem L{bpc, nbps, S, cwin, ORD, NST, H, CL, plan_smem ? plan_share : 0, plan_smem ? (ncoef0 + CL - 1) / CL + 1 : 0};
+    const int dpitch = L.dpitch();
     double *ring_s = smem + L.ring_off();
     double *D_s = smem + L.D_off();
     double *DI_s = smem + L.DI_off();
     double *DF_s = smem + L.DF_off();
-    unsigned long long *viol_s = reinterpret_cast<unsigned long long *>(smem + L.viol_off()); /* [2], per CTA */
-    double *sc_s = smem + L.sc_off();     /* rank 0: [0] initial cost, [1] final cost */
-    double *fall_s = smem + L.fall_off(); /* rank 0 holds the integrand of ALL breakpoints */
+    unsigned long long *viol_s = reinterpret_cast<unsigned long long *>(smem + L.viol_off());   /* [2] */
+    unsigned long long *violx_s = reinterpret_cast<unsigned long long *>(smem + L.violx_off()); /* rank 0: [2][CL] */
+    double *sc_s = smem + L.sc_off();     /* rank 0: [buf][0] initial cost, [buf][1] final cost */
+    double *fall_s = smem + L.fall_off(); /* rank 0: the integrand of ALL breakpoints [buf][nbps]; else this CTA's [buf][bpc] */
     double *t_s = smem + L.t_off();       /* rank 0: trapezoid terms of the scalar cost */
     double *dt_s = smem + L.dt_off();
     double *wf_s = smem + L.wf_off();     /* (dt[n-1] + dt[n])/2: the trapezoid rule as node weights */
     double *C_s = smem + L.C_off();
     unsigned long long *bar_s = reinterpret_cast<unsigned long long *>(smem + L.bar_off());
-    double *fall0 = cluster.map_shared_rank(fall_s, 0);
-    double *sc0 = cluster.map_shared_rank(sc_s, 0);
     const unsigned ring_a = smem_u32(ring_s);
     const unsigned STAGE_BYTES = (unsigned)L.stage_doubles() * 8u;
     const unsigned full_a = smem_u32(bar_s), empty_a = full_a + 8u * (unsigned)NST;
+    const unsigned ready_a = empty_a + 8u * (unsigned)NST; /* [2] rank 0: the other ranks' integrand / violation of buffer b arrived */
+    const unsigned free_a = ready_a + 16u;                 /* [2] other ranks: rank 0 is done with buffer b */
+    const int fpitch = rank == 0 ? nbps : bpc;
 
     /* mode 2 / mode 2: counts gate on != 0 (reference src/ntg.c:309-314) */
     const bool doI = PK::cb_icf != nullptr && T.nicf != 0;
@@ -189,6 +229,7 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL,
     const int NCW = NCT / 32;
     const bool service = (int)threadIdx.x >= NCT;
     const int lane = threadIdx.x & 31;
+    const int last_rank = (nbps - 1) / bpc;
 
     /* ---- once per CTA ---- */
     for (int i = threadIdx.x; i < nbps - 1; i += blockDim.x) dt_s[i] = __ldg(T.bps + i + 1) - __ldg(T.bps + i);
@@ -197,40 +238,57 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL,
         const double hi = n + 1 < nbps ? (__ldg(T.bps + n + 1) - __ldg(T.bps + n)) * 0.5 : 0.0;
         wf_s[n] = lo + hi;
     }
+    /* the second plan of the tables (ntg_kernel_args.h): entries of column cl at [hptr[cl], hptr[cl+1]) */
+    const int *hptr = T.plan_ptr + ncoef0 + 1;
     const int2 *plan = T.plan;
-    const int *plan_ptr = T.plan_ptr;
-    if (plan_smem) { /* the plan is re-read for every problem: keep it next to the data it indexes */
+    const int *plan_ptr = hptr;
+    int plan_shift = 0, col_shift = 0; /* plan[e - plan_shift], plan_ptr[cl - col_shift] */
+    if (plan_smem) { /* this CTA's columns only; re-read for every problem: keep it next to the data it indexes */
         int2 *pl_s = reinterpret_cast<int2 *>(smem + L.plan_off());
-        int *pp_s = reinterpret_cast<int *>(pl_s + T.plan_n);
-        for (int i = threadIdx.x; i < T.plan_n; i += blockDim.x) pl_s[i] = __ldg(T.plan + i);
-        for (int i = threadIdx.x; i <= T.ncoef[0]; i += blockDim.x) pp_s[i] = __ldg(T.plan_ptr + i);
+        int *pp_s = reinterpret_cast<int *>(pl_s + plan_share);
+        const int e0 = __ldg(hptr + c_lo), e1 = __ldg(hptr + c_hi);
+        for (int i = threadIdx.x; i < e1 - e0; i += blockDim.x) pl_s[i] = __ldg(T.plan + e0 + i);
+        for (int i = threadIdx.x; i <= c_hi - c_lo; i += blockDim.x) pp_s[i] = __ldg(hptr + c_lo + i);
         plan = pl_s;
         plan_ptr = pp_s;
+        plan_shift = e0;
+        col_shift = c_lo;
     }
     if (threadIdx.x == 0) {
-        sc_s[0] = sc_s[1] = 0.0;
+        sc_s[0] = sc_s[1] = sc_s[2] = sc_s[3] = 0.0;
         viol_s[0] = 0ull;
         viol_s[1] = 0ull;
+        for (int i = 0; i < 2 * CL; i++) violx_s[i] = 0ull;
         for (int i = 0; i < NST; i++) {
             mbar_init(full_a + 8u * (unsigned)i, (unsigned)NCW); /* one arrival per compute warp */
             mbar_init(empty_a + 8u * (unsigned)i, 1u);           /* the service warp */
         }
+        for (int b = 0; b < 2; b++) {
+            mbar_init(ready_a + 8u * (unsigned)b, (unsigned)(CL - 1)); /* the service warps of the other ranks */
+            mbar_init(free_a + 8u * (unsigned)b, 1u);                  /* the service warp of rank 0 */
+        }
     }
 
-    /* ---- once per thread: its breakpoint, its table slice ---- */
+    /* ---- once per thread: its breakpoint (own or halo), its table slice ---- */
     const int bp0 = rank * bpc;
-    const int lbp = threadIdx.x; /* breakpoint index inside this CTA */
-    const int bp = bp0 + lbp;
+    const int lbp = threadIdx.x;
     const int cnt = nbps - bp0 < bpc ? (nbps - bp0 > 0 ? nbps - bp0 : 0) : bpc; /* breakpoints of this CTA */
-    const bool active = !service && lbp < cnt;
+    const bool own = !service && lbp < cnt;
+    /* lanes [cnt, cnt + 2H): H breakpoints in front of and H behind this CTA's range -- their cost
+     * derivatives are computed here a second time, so that a quadrature chain never leaves the CTA */
+    const int hidx = lbp - cnt;
+    const int bp = own ? bp0 + lbp : (hidx < H ? bp0 - H + hidx : bp0 + cnt + hidx - H);
+    const bool halo = !service && !own && hidx < 2 * H && bp >= 0 && bp < nbps;
+    const bool live = own || halo;
+    const int dpos = own ? H + lbp : (hidx < H ? hidx : cnt + hidx); /* position in a row of D */
     double Bt[NB];
     int off0 = 0;
     {
-        off0 = active ? __ldg(T.off[0] + bp) : 0;
+        off0 = live ? __ldg(T.off[0] + bp) : 0;
 #pragma unroll
         for (int k = 0; k < ORD; k++)
 #pragma unroll
-            for (int d = 0; d < MD0; d++) Bt[k * MD0 + d] = active ? __ldg(T.Bt[0] + (size_t)(k * MD0 + d) * nbps + bp) : 0.0;
+            for (int d = 0; d < MD0; d++) Bt[k * MD0 + d] = live ? __ldg(T.Bt[0] + (size_t)(k * MD0 + d) * nbps + bp) : 0.0;
     }
 
     /* this CTA only needs the coefficient windows of ITS breakpoints: per output the range
@@ -238,11 +296,11 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL,
     __shared__ int win_s[2];
     if (threadIdx.x == 0) { win_s[0] = 0x7fffffff; win_s[1] = -1; }
     __syncthreads();
-    if (active) {
+    if (live) {
         atomicMin(&win_s[0], off0);
         atomicMax(&win_s[1], off0);
     }
-    __syncthreads(); /* also publishes the mbarrier initialisation */
+    cluster.sync(); /* publishes the mbarrier initialisation, cluster-wide (remote arrivals below) */
     const int w0 = win_s[0];
     const int wl = win_s[1] + ORD - w0;
 
@@ -253,15 +311,16 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL,
     auto tile_base = [&](int p) { return ((size_t)p * T.ncnln + T.nnlic) * S + (size_t)rank * T.nnltc * S * bpc; };
     const unsigned n_st = (unsigned)(ORD * cnt);
 
-    cluster.barrier_arrive(); /* "D is free" for the first problem */
-
     if (service) {
         /* =================== the service warp: drain stages, finish the scalar cost =================== */
         unsigned st = 0, ph = 0;
         int prev_st = -1;
         int buf = 0;
+        unsigned use = 0; /* how often buffer `buf` has been used before: use = (iteration / 2) */
+        int it = 0;
         const unsigned stage_flip = n_st & 1u; /* does the parity of a stage's first element flip from stage to stage? */
-        for (int p = clid; p < P; p += ncl, buf ^= 1) {
+        for (int p = clid; p < P; p += ncl, buf ^= 1, it++) {
+            use = (unsigned)(it >> 1);
             /* ONE bulk copy per stage, issued by an elected lane from uniform registers.  (A first version
              * copied row by row, each row from its own lane: the compiler serialises per-lane bulk copies
              * through R2UR, ~150 dependent instructions per stage on a single warp, and a thread sustains
@@ -291,13 +350,31 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL,
                 gp += n_st;
                 par ^= stage_flip;
             }
-            cluster.barrier_wait();   /* D free (matches the compute warps' sequence) */
-            cluster.barrier_arrive();
-            cluster.barrier_wait();   /* D, integrand, end-point terms and violations of problem p are complete */
-            if (rank == 0) {
+            /* the compute warps have written this problem's integrand, end-point costs and violation */
+            named_bar_sync(3, NCT + 32);
+            if (rank != 0) {
+                /* forward them to rank 0 (stores into ITS shared memory), once rank 0 is done with what this
+                 * buffer held two problems ago.  The cluster-scope release behind the arrival costs a
+                 * MEMBAR.GPU (~1.7k cycles): it is paid here, by a warp that has nothing else to do while
+                 * the compute warps run the quadrature -- they never touch a cluster barrier. */
+                mbar_wait_cluster(free_a + 8u * (unsigned)buf, (use & 1u) ^ 1u);
+                double *f0 = cluster.map_shared_rank(fall_s, 0) + (size_t)buf * nbps + bp0;
+                const double *fl = fall_s + (size_t)buf * bpc;
+                if (doU)
+                    for (int i = lane; i < cnt; i += 32) f0[i] = fl[i];
+                if (lane == 0) {
+                    cluster.map_shared_rank(violx_s, 0)[buf * CL + rank] = viol_s[buf];
+                    viol_s[buf] = 0ull;
+                    if (doF && rank == last_rank) cluster.map_shared_rank(sc_s, 0)[buf * 2 + 1] = sc_s[buf * 2 + 1];
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote_release(map_to_rank(ready_a + 8u * (unsigned)buf, 0));
+            } else {
+                if (CL > 1) mbar_wait_cluster(ready_a + 8u * (unsigned)buf, use & 1u);
                 /* IntegrateVector TRAPEZOID (src/integrator.c:21-24): a sequential chain over all breakpoints */
+                const double *fp = fall_s + (size_t)buf * nbps;
                 if (doU) {
-                    for (int i = lane; i < nbps - 1; i += 32) t_s[i] = (dt_s[i] * (fall_s[i + 1] + fall_s[i])) / 2;
+                    for (int i = lane; i < nbps - 1; i += 32) t_s[i] = (dt_s[i] * (fp[i + 1] + fp[i])) / 2;
                 }
                 __syncwarp();
                 if (lane == 0) {
@@ -306,26 +383,25 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL,
 #pragma unroll 8
                         for (int i = 0; i < nbps - 1; i++) In = In + t_s[i];
                     }
-                    unsigned long long vb = 0ull;
-                    for (int r = 0; r < CL; r++) {
-                        unsigned long long *vr = cluster.map_shared_rank(viol_s, r) + buf;
-                        const unsigned long long v = *vr;
+                    unsigned long long vb = viol_s[buf];
+                    viol_s[buf] = 0ull;
+                    for (int r = 1; r < CL; r++) {
+                        const unsigned long long v = violx_s[buf * CL + r];
                         vb = v > vb ? v : vb;
-                        *vr = 0ull; /* next written two problems later, behind two cluster barriers */
                     }
-                    const double y = (sc_s[0] + In) + sc_s[1]; /* y = I + In + F, src/ntg.c:328 */
+                    const double y = (sc_s[buf * 2 + 0] + In) + sc_s[buf * 2 + 1]; /* y = I + In + F, src/ntg.c:328 */
                     A.f[p] = y;
                     if (want_result<PEERS>(A)) {
                         put_result<PEERS>(A, (size_t)p, 0, y);
                         put_result<PEERS>(A, (size_t)p, 1, __longlong_as_double((long long)vb));
                     }
+                    for (int r = 1; r < CL; r++) mbar_arrive_remote_relaxed(map_to_rank(free_a + 8u * (unsigned)buf, r));
                 }
                 __syncwarp();
             }
-            cluster.barrier_arrive(); /* done with D / integrand of problem p */
         }
         bulk_wait_all();
-        cluster.barrier_wait();
+        cluster.sync(); /* nobody exits while a neighbour may still store into / arrive on its shared memory */
         return;
     }
 
@@ -346,7 +422,7 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL,
     int buf = 0;
     for (int p = clid; p < P; p += ncl, buf ^= 1) {
         cp_async_wait_all();
-        named_bar_sync(1, NCT); /* this problem's coefficients landed */
+        named_bar_sync(1, NCT); /* this problem's coefficients landed; every warp is past the previous quadrature: D is free */
 
         double z[NZ];
         double *zp[NOUT];
@@ -359,7 +435,7 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL,
             double acc[MD0];
 #pragma unroll
             for (int d = 0; d < MD0; d++) acc[d] = 0.0;
-            if (active) {
+            if (live) {
 #pragma unroll
                 for (int k = 0; k < ORD; k++) {
                     const double ck = Cw[k];
@@ -397,11 +473,11 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL,
              * merges them and keeps every row's derivatives live (144 registers at CFG-5, spills) */
 #pragma unroll
             for (int l = 0; l < NZ; l++) asm volatile("" : "+d"(z[l]));
-            /* lanes past the CTA's last breakpoint run along on zeros (their table slice is zero); only
+            /* lanes that own no breakpoint run along (halo lanes on their own z, the rest on zeros); only
              * their stores are predicated off: no divergence in the stage loop */
             int mode = 2, i = bp;
             PK::cb_nltcf(&mode, &nstate, &i, cv, dfp, zp);
-            if (active) {
+            if (own) {
                 note_abort(A, mode);
                 st_stream(A.c + (size_t)p * T.ncnln + T.nnlic + (size_t)m * nbps + bp, cv[m]);
                 viol = fmax(viol, row_violation(cv[m], nl_bound(T, false, T.nnlic + m), nl_bound(T, true, T.nnlic + m)));
@@ -421,8 +497,8 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL,
                     const unsigned a0 = ring_a + st * STAGE_BYTES + ((unsigned)lbp + par) * 8u;
                     static_for<0, ORD>([&](auto kc) {
                         constexpr int k = decltype(kc)::value;
-                        /* (rows are contiguous: a lane past the CTA's last breakpoint must not store) */
-                        if (active && (!(HOT_DBG & 4) || v[k] == 1.2345e300)) sts_f64<0>(a0 + (unsigned)k * cnt8, v[k]);
+                        /* (rows are contiguous: a lane that owns no breakpoint must not store) */
+                        if (own && (!(HOT_DBG & 4) || v[k] == 1.2345e300)) sts_f64<0>(a0 + (unsigned)k * cnt8, v[k]);
                     });
                     if (!(HOT_DBG & 1)) fence_proxy_async_smem();
                 }
@@ -432,7 +508,7 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL,
             });
         });
 
-        if (active) {
+        if (own) {
             /* nonlinear initial constraints (breakpoint 0), src/constraints.c:88-117 */
             if constexpr (PK::cb_nlicf != nullptr && PK::kNnlic > 0) {
                 if (doCI && bp == 0) {
@@ -492,10 +568,9 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL,
             if (viol > 0.0) atomicMax(viol_s + buf, (unsigned long long)__double_as_longlong(viol));
         }
 
-        cluster.barrier_wait(); /* every CTA finished the quadrature of the previous problem: D is free */
-
-        if (active) {
-            /* unintegrated (trajectory) cost, src/cost.c:99-132 */
+        if (live) {
+            /* unintegrated (trajectory) cost, src/cost.c:99-132; halo lanes repeat a neighbour's breakpoint
+             * for the band D only */
             if constexpr (PK::cb_ucf != nullptr) {
                 if (doU) {
                     double fv = 0.0;
@@ -504,15 +579,19 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL,
                     for (int l = 0; l < NZ; l++) df[l] = 0.0;
                     int mode = 2, i = bp;
                     PK::cb_ucf(&mode, &nstate, &i, &fv, df, zp);
-                    note_abort(A, mode);
-                    fall0[bp] = fv; /* distributed shared memory: rank 0 collects the integrand */
-                    double *Dp = D_s + lbp;
+                    if (own) {
+                        note_abort(A, mode);
+                        fall_s[(size_t)buf * fpitch + (rank == 0 ? bp : lbp)] = fv; /* the service warp forwards it to rank 0 */
+                    }
+                    double *Dp = D_s + dpos;
                     band_from_regs<PK, true, true>(T, Bt, df, [&](auto, auto, double v) {
                         *Dp = v;
-                        Dp += bpc;
+                        Dp += dpitch;
                     });
                 }
             }
+        }
+        if (own) {
             /* initial cost (breakpoint 0: cluster rank 0), src/cost.c:4-36 */
             if constexpr (PK::cb_icf != nullptr) {
                 if (doI && bp == 0) {
@@ -523,7 +602,7 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL,
                     int mode = 2;
                     PK::cb_icf(&mode, &nstate, &fv, df, zp);
                     note_abort(A, mode);
-                    sc0[0] = fv;
+                    sc_s[buf * 2 + 0] = fv;
                     double *Dp = DI_s;
                     band_from_regs<PK, true, true>(T, Bt, df, [&](auto, auto, double v) { *Dp++ = v; });
                 }
@@ -538,78 +617,55 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL,
                     int mode = 2;
                     PK::cb_fcf(&mode, &nstate, &fv, df, zp);
                     note_abort(A, mode);
-                    sc0[1] = fv;
+                    sc_s[buf * 2 + 1] = fv;
                     double *Dp = DF_s;
                     band_from_regs<PK, true, true>(T, Bt, df, [&](auto, auto, double v) { *Dp++ = v; });
                 }
             }
         }
-        cluster.barrier_arrive();
-        cluster.barrier_wait(); /* every CTA's D, integrand and scalars are visible cluster-wide */
+        named_bar_arrive(3, NCT + 32); /* integrand / end-point costs / violation of this problem: over to the service warp */
+        named_bar_sync(2, NCT);        /* this CTA's D (own breakpoints and halo) is complete */
 
         /* ------- phase B: one trapezoid chain per gradient column (IntegrateFMatrixCols TRAPEZOID,
-         * src/integrator.c:44-48, on the band of src/cost.c:118-132; ascending breakpoint).  The columns
-         * are dealt in contiguous ranges, so a CTA mostly walks ITS OWN D; a column whose support crosses
-         * the boundary reads the neighbour's through distributed shared memory.  Then Vector3Add,
-         * src/ntg.c:329. ------- */
+         * src/integrator.c:44-48, on the band of src/cost.c:118-132; ascending breakpoint), walking the
+         * host-built plan.  Every chain of this CTA's columns stays inside its own D (own breakpoints +
+         * halo): no distributed shared memory, no cluster barrier.  Then Vector3Add, src/ntg.c:329. ------- */
         {
-            const int ncoef0 = T.ncoef[0];
-            const int last_rank = (nbps - 1) / bpc;
             const int off_last = __ldg(T.off[0] + nbps - 1);
-            constexpr int jpitch_ord = ORD;
-            const int jpitch = jpitch_ord * bpc; /* one output's block of D */
-            const int c_lo = (int)(((long long)ncoef0 * rank) / CL), c_hi = (int)(((long long)ncoef0 * (rank + 1)) / CL);
+            const int jpitch = ORD * dpitch; /* one output's block of D */
             for (int cl = c_lo + (int)threadIdx.x; cl < c_hi && !(HOT_DBG & 8); cl += NCT) {
                 double gU[NOUT], dcur[NOUT];
 #pragma unroll
                 for (int j = 0; j < NOUT; j++) { gU[j] = 0.0; dcur[j] = 0.0; }
+                int e = plan_ptr[cl - col_shift] - plan_shift;
+                const int eend = plan_ptr[cl + 1 - col_shift] - plan_shift;
                 if (doU && !PK::kExact) {
-                    /* fast variant: sum_n Wf[n]*D[n] over the plan's in-band entries (the band is zero at
-                     * both ends of a column's support, so the node-weight form needs no end corrections) */
-                    const int eend = plan_ptr[cl + 1];
+                    /* fast variant: sum_n Wf[n]*D[n] over the in-band entries (the band is zero at both ends of
+                     * a column's support, so the node-weight form needs no end corrections) */
 #pragma unroll 4
-                    for (int e = plan_ptr[cl]; e < eend; e++) {
+                    for (; e < eend; e++) {
                         const int2 en = plan[e];
-                        const int o24 = en.y & 0xffffff, r = en.y >> 24;
-                        if (o24 == 0xffffff) continue;
                         const double w = wf_s[en.x];
-                        if (r == rank) {
 #pragma unroll
-                            for (int j = 0; j < NOUT; j++) gU[j] = gU[j] + w * D_s[j * jpitch + o24];
-                        } else {
-                            const double *base = cluster.map_shared_rank(D_s, r) + o24;
-#pragma unroll
-                            for (int j = 0; j < NOUT; j++) gU[j] = gU[j] + w * base[j * jpitch];
-                        }
+                        for (int j = 0; j < NOUT; j++) gU[j] = gU[j] + w * D_s[j * jpitch + en.y];
                     }
                 } else if (doU) {
-                    int e = plan_ptr[cl];
-                    const int eend = plan_ptr[cl + 1];
                     if (e < eend) {
                         int2 en = plan[e];
-                        {
-                            const int o24 = en.y & 0xffffff, r = en.y >> 24;
-                            if (o24 != 0xffffff) {
-                                const double *base = (r == rank ? D_s : cluster.map_shared_rank(D_s, r)) + o24;
+                        if (en.y >= 0) {
 #pragma unroll
-                                for (int j = 0; j < NOUT; j++) dcur[j] = base[j * jpitch];
-                            }
+                            for (int j = 0; j < NOUT; j++) dcur[j] = D_s[j * jpitch + en.y];
                         }
                         for (e++; e < eend; e++) {
                             en = plan[e];
-                            const int o24 = en.y & 0xffffff, r = en.y >> 24;
                             const double dt = dt_s[en.x - 1];
                             double dn[NOUT];
-                            if (o24 == 0xffffff) {
+                            if (en.y < 0) {
 #pragma unroll
                                 for (int j = 0; j < NOUT; j++) dn[j] = 0.0;
-                            } else if (r == rank) {
-#pragma unroll
-                                for (int j = 0; j < NOUT; j++) dn[j] = D_s[j * jpitch + o24];
                             } else {
-                                const double *base = cluster.map_shared_rank(D_s, r) + o24;
 #pragma unroll
-                                for (int j = 0; j < NOUT; j++) dn[j] = base[j * jpitch];
+                                for (int j = 0; j < NOUT; j++) dn[j] = D_s[j * jpitch + en.y];
                             }
 #pragma unroll
                             for (int j = 0; j < NOUT; j++) {
@@ -624,16 +680,15 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int CL,
                 for (int j = 0; j < NOUT; j++) {
                     const int s0 = j * ORD; /* jk0_j: every output has the same order */
                     double gI = 0.0, gF = 0.0;
-                    if (doI && cl < ORD) gI = cluster.map_shared_rank(DI_s, 0)[s0 + cl]; /* offset 0, src/colloc.c:254 */
-                    if (doF && kF >= 0 && kF < ORD) gF = cluster.map_shared_rank(DF_s, last_rank)[s0 + kF];
+                    if (doI && cl < ORD) gI = DI_s[s0 + cl];              /* offset 0, src/colloc.c:254; rank 0's columns */
+                    if (doF && kF >= 0 && kF < ORD) gF = DF_s[s0 + kF];   /* the last rank's columns */
                     st_stream(A.g + (size_t)p * nC + (size_t)j * ncoef0 + cl, (gI + gU[j]) + gF);
                 }
             }
         }
-        cluster.barrier_arrive(); /* this CTA no longer reads anybody's D */
     }
     cp_async_wait_all();
-    cluster.barrier_wait(); /* nobody may exit while a neighbour still reads its shared memory */
+    cluster.sync(); /* nobody exits while a neighbour may still store into / arrive on its shared memory */
 }
 
 /* does this launch qualify for the steady-state cluster kernel? */
@@ -646,25 +701,30 @@ int launch_eval_cluster_hot(const ntgb_launch *L)
         const ntgb_devtab &T = L->tab;
         const ntgb_eval_args &a = L->args;
         const int nbps = T.nbps, P = a.P;
-        if (!devtab_one_table(T) || nbps > 8 * 224) return -1001;
+        if (!devtab_one_table(T) || T.plan == nullptr || T.plan_halo < 0) return -1001;
         const bool hot = a.mode_obj == 2 && a.mode_con == 2 && a.jac_layout == NTGB_JAC_BAND && a.J != nullptr &&
                          a.f != nullptr && a.g != nullptr && a.c != nullptr && a.Z == nullptr && T.nnltc == PK::kNnltc &&
                          ((uintptr_t)a.J & 15u) == 0;
         if (!hot) return -1001;
         for (int j = 0; j < T.nout; j++)
             if (T.order[j] != PK::kMaxOrd) return -1001;
-        int CL, bpc;
-        ntgb_cluster_geometry(nbps, &CL, &bpc);
-        if (T.plan == nullptr || T.plan_cl != CL || T.plan_bpc != bpc) return -1001;
-        const int block = (bpc + 31) / 32 * 32 + 32; /* + the service warp */
-        if (block > 256 || T.band_tile != bpc) return -1001;
-        /* as many ring stages as fit (at least 3); the plan moves to global memory if it must */
+        /* cluster geometry, halo and plans were decided when the tables were built (ntg_core.cu) */
+        const int CL = T.plan_cl, bpc = T.plan_bpc, H = T.plan_halo;
+        if (CL < 2 || T.band_tile != bpc || bpc + 2 * H > 224) return -1001;
+        const int block = (bpc + 2 * H + 31) / 32 * 32 + 32; /* + the service warp */
+        /* the widest share of the plan any CTA of the cluster copies to shared memory */
+        const int plan_share = T.plan_share > 0 ? T.plan_share : 1;
+        /* as many ring stages as fit, but fewer than one problem has: the compute warps must not be able
+         * to finish the NEXT problem's rows before the service warp has handed this one's integrand over */
+        constexpr int NS = PK::kNnltc * PK::kNout;
+        if (NS < 3) return -1001;
         int nst = 8, plan_smem = 1;
         if (const char *e = getenv("NTG_B200_HOT_STAGES")) nst = atoi(e);
+        if (nst > NS - 1) nst = NS - 1;
         if (nst < 2) nst = 2;
         if (nst > 16) nst = 16;
-        ClusterHotSmem lay{bpc, nbps, T.S, T.plan_cwin, PK::kMaxOrd, nst, T.plan_n, T.ncoef[0]};
-        while (lay.nst > 3 && lay.bytes() > (size_t)L->max_smem_optin) lay.nst--;
+        ClusterHotSmem lay{bpc, nbps, T.S, T.plan_cwin, PK::kMaxOrd, nst, H, CL, plan_share, (T.ncoef[0] + CL - 1) / CL + 1};
+        while (lay.nst > 2 && lay.bytes() > (size_t)L->max_smem_optin) lay.nst--;
         if (lay.bytes() > (size_t)L->max_smem_optin) {
             lay.plan_n = 0;
             lay.plan_cols = 0;
@@ -692,7 +752,7 @@ int launch_eval_cluster_hot(const ntgb_launch *L)
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        return (int)cudaLaunchKernelEx(&cfg, kern, T, a, CL, bpc, T.plan_cwin, plan_smem, lay.nst);
+        return (int)cudaLaunchKernelEx(&cfg, kern, T, a, T.plan_cwin, plan_smem, lay.nst, plan_share);
     }
 }
 

@@ -62,16 +62,26 @@ typedef struct ntgb_devtab {
      * [NTGB_SCHED_BLOCK+1] (into the column list), then the column list [nC+1]. */
     int sched_G;
     int sched_ns[8];
+    /* steady-state cluster kernel (K1c/H): a second plan follows the first in the same arrays --
+     * plan_ptr[ncoef+1 .. 2*ncoef+2) and plan[plan_n ..) -- in which every column belongs to ONE
+     * CTA (columns are dealt in contiguous ranges, rank r owns [ncoef*r/CL, ncoef*(r+1)/CL)) and
+     * .y = k*(bpc + 2*plan_halo) + (n - r*bpc + plan_halo) is the position inside THAT CTA's D, whose
+     * rows carry plan_halo extra breakpoints on both sides (computed redundantly by the CTA, so that
+     * the quadrature never reads a neighbour's shared memory), or -1 outside the band; the plan of
+     * a `fast` pack lists in-band entries only.  plan_halo < 0: no such plan. */
+    int plan_halo;
+    int plan_share;                 /* second plan: most entries any one rank owns */
     const int *sched;
 } ntgb_devtab;
 
 #define NTGB_SCHED_BLOCK 256
 
-/* cluster geometry of K1c for a horizon of nbps breakpoints (shared by core and launcher) */
-static inline void ntgb_cluster_geometry(int nbps, int *CL, int *bpc)
+/* cluster geometry of K1c for a horizon of nbps breakpoints: at most `per_cta` (<= 224) breakpoints per
+ * CTA -- 7 warps pinned to breakpoints + 1 service warp = 256 threads.  Decided once at create time
+ * (plan_cl, plan_bpc); the launchers read it from the tables. */
+static inline void ntgb_cluster_geometry(int nbps, int per_cta, int *CL, int *bpc)
 {
-    /* at most 224 breakpoints per CTA: 7 warps pinned to breakpoints + 1 service warp = 256 threads */
-    int cl = nbps <= 2 * 224 ? 2 : (nbps <= 4 * 224 ? 4 : 8);
+    int cl = nbps <= 2 * per_cta ? 2 : (nbps <= 4 * per_cta ? 4 : 8);
     *CL = cl;
     *bpc = (nbps + cl - 1) / cl;
 }

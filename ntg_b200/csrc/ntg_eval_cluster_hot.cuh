@@ -50,9 +50,6 @@
 
 #include "ntg_eval_cluster.cuh"
 
-#ifndef HOT_DBG
-#define HOT_DBG 0
-#endif
 namespace ntgb {
 
 
@@ -162,6 +159,16 @@ struct ClusterHotSmem {
     __host__ __device__ size_t bytes() const { return (plan_off() + plan_n) * 8 + (size_t)(plan_cols + 2) * 4 + 16; }
 };
 
+/* outputs per ring stage: fewer, larger stages = fewer handshakes and larger bulk copies */
+#ifndef HOT_JPS
+#define HOT_JPS 2
+#endif
+template <class PK>
+__host__ __device__ constexpr int hot_jps()
+{
+    return (PK::kNout % HOT_JPS == 0) ? HOT_JPS : 1;
+}
+
 /* band values of ONE output from the register table (every output shares table 0) */
 template <class PK, int J, unsigned long long MASK>
 __device__ __forceinline__ void band_one_output(const double *Bt, const double *df, double (&v)[PK::kMaxOrd])
@@ -189,6 +196,8 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int cwi
     constexpr int ORD = PK::kMaxOrd;
     constexpr int NB = ORD * MD0; /* ONE table */
     constexpr int NCON = PK::kNnltc;
+    constexpr int JPS = hot_jps<PK>();  /* outputs per stage */
+    constexpr int NJG = NOUT / JPS;     /* stages per constraint row */
     extern __shared__ __align__(16) double smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
@@ -196,7 +205,7 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int cwi
     const int nbps = T.nbps, nC = T.nC, P = A.P, S = T.S, ncoef0 = T.ncoef[0];
     /* quadrature columns of this CTA: a contiguous range, so that the chains stay inside its own D */
     const int c_lo = (int)(((long long)ncoef0 * rank) / CL), c_hi = (int)(((long long)ncoef0 * (rank + 1)) / CL);
-    const ClusterHotSmem L{bpc, nbps, S, cwin, ORD, NST, H, CL, plan_smem ? plan_share : 0, plan_smem ? (ncoef0 + CL - 1) / CL + 1 : 0};
+    const ClusterHotSmem L{bpc, nbps, S, cwin, ORD * JPS, NST, H, CL, plan_smem ? plan_share : 0, plan_smem ? (ncoef0 + CL - 1) / CL + 1 : 0};
     const int dpitch = L.dpitch();
     double *ring_s = smem + L.ring_off();
     double *D_s = smem + L.D_off();
@@ -283,6 +292,13 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int cwi
     const int dpos = own ? H + lbp : (hidx < H ? hidx : cnt + hidx); /* position in a row of D */
     double Bt[NB];
     int off0 = 0;
+    /* active-variable mask of this thread's breakpoint class, bit iz_j + d (updateZ fills listed variables only) */
+    unsigned long long zmask = 0ull;
+    static_for<0, NOUT>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        const unsigned mk = T.avmask[(bp == 0 ? 1 : 0) | (bp == nbps - 1 ? 2 : 0)][j];
+        zmask |= (unsigned long long)(mk & ((1u << MD0) - 1u)) << pk_iz<PK>(j);
+    });
     {
         off0 = live ? __ldg(T.off[0] + bp) : 0;
 #pragma unroll
@@ -307,9 +323,9 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int cwi
     const int ncl = (int)(gridDim.x / CL); /* clusters in the grid */
     const int clid = (int)(blockIdx.x / CL);
     /* element index (from A.J) of this CTA's tile of problem p's trajectory rows (tiled band layout,
-     * include/ntg_b200.h): [m][slot][breakpoint of the tile], n_st = ORD*cnt elements per stage */
+     * include/ntg_b200.h): [m][slot][breakpoint of the tile], n_st = JPS*ORD*cnt elements per stage */
     auto tile_base = [&](int p) { return ((size_t)p * T.ncnln + T.nnlic) * S + (size_t)rank * T.nnltc * S * bpc; };
-    const unsigned n_st = (unsigned)(ORD * cnt);
+    const unsigned n_st = (unsigned)(JPS * ORD * cnt);
 
     if (service) {
         /* =================== the service warp: drain stages, finish the scalar cost =================== */
@@ -328,14 +344,14 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int cwi
             double *gp = A.J + tile_base(p);              /* stage (m = 0, j = 0) of this CTA's tile */
             unsigned par = (unsigned)(tile_base(p) & 1);  /* parity of the stage's first element */
 #pragma unroll 1
-            for (int s = 0; s < NCON * NOUT; s++) {
+            for (int s = 0; s < NCON * NJG; s++) {
                 const unsigned sbase = ring_a + st * STAGE_BYTES;
                 const double *stage = ring_s + (size_t)st * L.stage_doubles(); /* element i at stage[i + par] */
                 const unsigned body = (n_st - par) & ~1u;
                 mbar_wait(full_a + 8u * st, ph);
                 const bool leader = elect_one();
                 if (leader) {
-                    if (body > 0 && !(HOT_DBG & 2)) bulk_store(gp + par, sbase + 16u * par, body * 8u);
+                    if (body > 0) bulk_store(gp + par, sbase + 16u * par, body * 8u);
                     bulk_commit();
                 }
                 /* odd head / tail elements of the block */
@@ -431,7 +447,6 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int cwi
             constexpr int j = decltype(jc)::value;
             constexpr int IZ = pk_iz<PK>(j);
             const double *Cw = C_s + j * wl + (off0 - w0);
-            const unsigned mask = T.avmask[(bp == 0 ? 1 : 0) | (bp == nbps - 1 ? 2 : 0)][j];
             double acc[MD0];
 #pragma unroll
             for (int d = 0; d < MD0; d++) acc[d] = 0.0;
@@ -444,7 +459,7 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int cwi
                 }
             }
 #pragma unroll
-            for (int d = 0; d < MD0; d++) z[IZ + d] = ((mask >> d) & 1u) ? acc[d] : 0.0;
+            for (int d = 0; d < MD0; d++) z[IZ + d] = ((zmask >> (IZ + d)) & 1ull) ? acc[d] : 0.0;
             zp[j] = &z[IZ];
         });
         named_bar_sync(1, NCT); /* everybody has read its window: fetch the next problem's */
@@ -483,25 +498,27 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int cwi
                 viol = fmax(viol, row_violation(cv[m], nl_bound(T, false, T.nnlic + m), nl_bound(T, true, T.nnlic + m)));
             }
             const bool clean = sp_clean<NZ>(dfc[m], PK::sp_nltcf(m));
-            static_for<0, NOUT>([&](auto jc) {
-                constexpr int j = decltype(jc)::value;
-                const unsigned ok = mbar_try_wait(empty_a + 8u * st, ph);
-                double v[ORD];
-                if (clean) band_one_output<PK, j, PK::sp_nltcf(m)>(Bt, dfc[m], v);
-                else band_one_output<PK, j, kDense>(Bt, dfc[m], v);
-                if (!ok) mbar_wait(empty_a + 8u * st, ph);
-                {
-                    /* value (k, this breakpoint) is element k*cnt + lbp of the stage, staged at + parity */
-                    constexpr unsigned STAGE_IDX = (unsigned)(m * NOUT + j);
-                    const unsigned par = pe ^ (STAGE_IDX & stage_flip & 1u);
-                    const unsigned a0 = ring_a + st * STAGE_BYTES + ((unsigned)lbp + par) * 8u;
+            static_for<0, NJG>([&](auto gc) {
+                constexpr int jg = decltype(gc)::value;
+                /* value (slot, this breakpoint) is element slot*cnt + lbp of the stage, staged at + parity */
+                constexpr unsigned STAGE_IDX = (unsigned)(m * NJG + jg);
+                const unsigned par = pe ^ (STAGE_IDX & stage_flip & 1u);
+                const unsigned a0 = ring_a + st * STAGE_BYTES + ((unsigned)lbp + par) * 8u;
+                unsigned ok = mbar_try_wait(empty_a + 8u * st, ph);
+                static_for<0, JPS>([&](auto jjc) {
+                    constexpr int jj = decltype(jjc)::value;
+                    constexpr int j = jg * JPS + jj;
+                    double v[ORD];
+                    if (clean) band_one_output<PK, j, PK::sp_nltcf(m)>(Bt, dfc[m], v);
+                    else band_one_output<PK, j, kDense>(Bt, dfc[m], v);
+                    if (jj == 0 && !ok) mbar_wait(empty_a + 8u * st, ph);
                     static_for<0, ORD>([&](auto kc) {
                         constexpr int k = decltype(kc)::value;
                         /* (rows are contiguous: a lane that owns no breakpoint must not store) */
-                        if (own && (!(HOT_DBG & 4) || v[k] == 1.2345e300)) sts_f64<0>(a0 + (unsigned)k * cnt8, v[k]);
+                        if (own) sts_f64<0>(a0 + (unsigned)(jj * ORD + k) * cnt8, v[k]);
                     });
-                    if (!(HOT_DBG & 1)) fence_proxy_async_smem();
-                }
+                });
+                fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(full_a + 8u * st);
                 if (++st == (unsigned)NST) { st = 0; ph ^= 1u; }
@@ -633,7 +650,7 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int cwi
         {
             const int off_last = __ldg(T.off[0] + nbps - 1);
             const int jpitch = ORD * dpitch; /* one output's block of D */
-            for (int cl = c_lo + (int)threadIdx.x; cl < c_hi && !(HOT_DBG & 8); cl += NCT) {
+            for (int cl = c_lo + (int)threadIdx.x; cl < c_hi; cl += NCT) {
                 double gU[NOUT], dcur[NOUT];
 #pragma unroll
                 for (int j = 0; j < NOUT; j++) { gU[j] = 0.0; dcur[j] = 0.0; }
@@ -716,14 +733,14 @@ int launch_eval_cluster_hot(const ntgb_launch *L)
         const int plan_share = T.plan_share > 0 ? T.plan_share : 1;
         /* as many ring stages as fit, but fewer than one problem has: the compute warps must not be able
          * to finish the NEXT problem's rows before the service warp has handed this one's integrand over */
-        constexpr int NS = PK::kNnltc * PK::kNout;
+        constexpr int NS = PK::kNnltc * PK::kNout / hot_jps<PK>();
         if (NS < 3) return -1001;
         int nst = 8, plan_smem = 1;
         if (const char *e = getenv("NTG_B200_HOT_STAGES")) nst = atoi(e);
         if (nst > NS - 1) nst = NS - 1;
         if (nst < 2) nst = 2;
         if (nst > 16) nst = 16;
-        ClusterHotSmem lay{bpc, nbps, T.S, T.plan_cwin, PK::kMaxOrd, nst, H, CL, plan_share, (T.ncoef[0] + CL - 1) / CL + 1};
+        ClusterHotSmem lay{bpc, nbps, T.S, T.plan_cwin, PK::kMaxOrd * hot_jps<PK>(), nst, H, CL, plan_share, (T.ncoef[0] + CL - 1) / CL + 1};
         while (lay.nst > 2 && lay.bytes() > (size_t)L->max_smem_optin) lay.nst--;
         if (lay.bytes() > (size_t)L->max_smem_optin) {
             lay.plan_n = 0;

@@ -371,8 +371,14 @@ def reference_example_packs() -> List[PackManifest]:
 
 def build_all(verbose: bool = False, force: bool = False) -> List[str]:
     built = [build_core(verbose, force)]
-    for m in repo_packs() + reference_example_packs():
-        built.append(build_pack(m, verbose, force))
+    packs = repo_packs() + reference_example_packs()
+    # the packs are independent translation units: one nvcc per host core, up to 8 at a time
+    from concurrent.futures import ThreadPoolExecutor
+    jobs = int(os.environ.get("NTG_B200_BUILD_JOBS", "0")) or min(8, len(os.sched_getaffinity(0)))
+    for m in packs:           # wrapper generation and the sparsity probes share files: serial
+        generate_wrapper(m, verbose)
+    with ThreadPoolExecutor(max_workers=max(1, jobs)) as ex:
+        built += list(ex.map(lambda m: build_pack(m, verbose, force), packs))
     return built
 
 

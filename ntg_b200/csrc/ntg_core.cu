@@ -1409,6 +1409,13 @@ static int eval_host_small(ntgb_problem *pb, const ntgb_eval_args *h, size_t jpe
     }
     const bool ov = h->mode_obj == 0 || h->mode_obj == 2, od = h->mode_obj == 1 || h->mode_obj == 2;
     const bool cv = h->mode_con == 0 || h->mode_con == 2, cd = h->mode_con == 1 || h->mode_con == 2;
+    if (z.j_bytes && !(h->J && jper) && off > z.j_off) {
+        /* a call WITHOUT a Jacobian whose carve-up reaches into the region the last Jacobian call
+         * zeroed (Z sits where J used to start): whatever this call writes there would be taken for
+         * out-of-band zeros by the next Jacobian call -- forget the region, it is cleared again then */
+        memset(z.buf + z.j_off, 0, z.j_bytes);
+        z.j_bytes = 0; z.j_layout = NTGB_JAC_NONE;
+    }
     if (h->J && jper) {
         /* out-of-band entries are zeros written once (src/ntg.c:218); a different layout, batch size
          * or place in the block means different band positions: clear the old and the new region */
@@ -1476,6 +1483,8 @@ int ntgb_eval_host(ntgb_problem *pb, const ntgb_eval_args *h)
         if (!grow) continue;
         double **ptrs[] = {&s.C, &s.f, &s.g, &s.c, &s.J, &s.Z, &s.result};
         for (double **pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
+        /* nothing is allocated now: if one of the allocations below fails, the next call starts over */
+        s.cap = 0; s.Jbytes = 0; s.hasZ = false; s.jac_layout = NTGB_JAC_NONE;
         const size_t cap = (size_t)chunk;
         CUDA_TRY(cudaMalloc((void **)&s.C, cap * d.nC * sizeof(double)));
         CUDA_TRY(cudaMalloc((void **)&s.f, cap * sizeof(double)));

@@ -199,24 +199,51 @@ void PrintiVector(const char *filename, int *f, int nf)
     if (cl) fclose(fp);
 }
 
+/* One page-locked, device-mapped staging block kept for the life of the process: a call copies the
+ * knots and coefficients into it, launches one thread and reads the derivatives back out of it --
+ * no allocation, no cudaMemcpy (examples/kincar.c:396-406 calls this in a loop over its output
+ * times).  There is no CPU path: every CUDA failure is fatal and says so. */
+static void spline_fail(const char *what, cudaError_t e)
+{
+    fprintf(stderr, "SplineInterp: %s: %s (there is no CPU path)\n", what, cudaGetErrorString(e));
+    abort();
+}
+
 void SplineInterp(double *f, double x, double *knots, int ninterv, double *coefs, int ncoefs, int order,
                   int mult, int maxderiv)
 {
+    static double *h_blk = nullptr, *d_blk = nullptr;
+    static size_t cap = 0;
     const int n = ninterv * (order - mult) + mult;
-    assert(n == ncoefs);
-    assert(order <= PGS_MAXK && maxderiv <= order);
-    double *d = nullptr;
-    const size_t nk = (size_t)ninterv + 1, total = nk + n + (n + order) + maxderiv;
-    if (cudaMalloc((void **)&d, total * sizeof(double)) != cudaSuccess) {
-        fprintf(stderr, "SplineInterp: no CUDA device / out of memory (there is no CPU path)\n");
+    if (n != ncoefs || ninterv < 1 || order < 1 || order > PGS_MAXK || maxderiv < 1 || maxderiv > order ||
+        mult < 0 || mult >= order) {
+        fprintf(stderr, "SplineInterp: bad spline description (ninterv %d order %d mult %d maxderiv %d ncoefs %d; "
+                        "need ncoefs = ninterv*(order-mult)+mult, maxderiv <= order <= %d)\n",
+                ninterv, order, mult, maxderiv, ncoefs, PGS_MAXK);
         abort();
     }
-    double *dk = d, *dc = d + nk, *daug = dc + n, *df = daug + (n + order);
-    cudaMemcpy(dk, knots, nk * sizeof(double), cudaMemcpyHostToDevice);
-    cudaMemcpy(dc, coefs, (size_t)n * sizeof(double), cudaMemcpyHostToDevice);
+    const size_t nk = (size_t)ninterv + 1, total = nk + n + (n + order) + maxderiv;
+    if (total > cap) {
+        if (h_blk) cudaFreeHost(h_blk);
+        h_blk = nullptr;
+        cap = 0;
+        const size_t want = total < 4096 ? 4096 : 2 * total;
+        cudaError_t e = cudaHostAlloc((void **)&h_blk, want * sizeof(double), cudaHostAllocMapped);
+        if (e != cudaSuccess) spline_fail("no CUDA device / cannot allocate the staging block", e);
+        e = cudaHostGetDevicePointer((void **)&d_blk, h_blk, 0);
+        if (e != cudaSuccess) spline_fail("cudaHostGetDevicePointer", e);
+        cap = want;
+    }
+    double *hk = h_blk, *hc = hk + nk, *hf = hc + n + (n + order);
+    memcpy(hk, knots, nk * sizeof(double));
+    memcpy(hc, coefs, (size_t)n * sizeof(double));
+    double *dk = d_blk, *dc = dk + nk, *daug = dc + n, *df = daug + (n + order);
     k_spline_single<<<1, 1>>>(dk, ninterv, dc, order, mult, maxderiv, x, daug, df);
-    cudaMemcpy(f, df, (size_t)maxderiv * sizeof(double), cudaMemcpyDeviceToHost);
-    cudaFree(d);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) spline_fail("kernel launch", e);
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) spline_fail("kernel execution", e);
+    memcpy(f, hf, (size_t)maxderiv * sizeof(double));
 }
 
 void ntg(int nout, double *bps, int nbps, int *kninterv, double **knots, int *order, int *mult, int *maxderiv,

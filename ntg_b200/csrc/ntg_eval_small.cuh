@@ -35,10 +35,6 @@
 
 #include "ntg_eval_kernel.cuh"
 
-#ifndef NTG_DBG
-#define NTG_DBG 0 /* scratch experiments: 1 skip phase B, 2 no Jacobian stores, 4 no phase-A shared stores */
-#endif
-
 namespace ntgb {
 
 template <class PK>
@@ -71,10 +67,16 @@ struct SmallSmem {
     __host__ __device__ size_t DF_off() const { return DI_off() + even((size_t)GR * S); }          /* [GR][S]        */
     __host__ __device__ size_t cI_off() const { return DF_off() + even((size_t)GR * S); }          /* [GR]           */
     __host__ __device__ size_t cF_off() const { return cI_off() + even(GR); }                      /* [GR]           */
-    __host__ __device__ size_t dt_off() const { return cF_off() + even(GR); }                      /* wt, Wf: [2][pitch + 2] */
+    __host__ __device__ size_t res_off() const { return cF_off() + even(GR); }                     /* [GR][2] (objective, violation) */
+    __host__ __device__ size_t dt_off() const { return res_off() + 2 * (size_t)GR; }               /* wt, Wf: [2][pitch + 2] */
     __host__ __device__ size_t C_off() const { return dt_off() + 2 * (size_t)(pitch() + 2); }      /* [2][GR*nC]     */
     __host__ __device__ size_t seg_off() const { return C_off() + 2 * even((size_t)GR * nC); }     /* ints, see the kernel */
-    __host__ __device__ size_t bytes() const { return seg_off() * 8 + (2 * (size_t)segtot + 4 + (size_t)(nC + 1) * 10) * 4 + 8; }
+    __host__ __device__ size_t bytes() const
+    {
+        /* ints: run tables, cost run, chain table, column list; then (8-byte aligned) the peer table pointers */
+        const size_t ints = 2 * (size_t)segtot + 4 + (size_t)(nC + 1) * 10;
+        return seg_off() * 8 + ((ints + 1) & ~(size_t)1) * 4 + NTGB_MAXPEERS * 8 + 8;
+    }
 };
 
 __device__ __forceinline__ void cp_async8(double *dst_smem, const double *src)
@@ -249,7 +251,6 @@ __device__ __forceinline__ void emit_rows_layout(const ntgb_devtab &T, const ntg
                 constexpr int SF = PK::kNout * PK::kMaxOrd;
                 band_from_regs<PK, FULL, ONE, MASK>(T, Bt, dfc[m], [&](auto jc, auto kc, double v) {
                     constexpr int slot = m * SF + decltype(jc)::value * PK::kMaxOrd + decltype(kc)::value;
-                    if ((NTG_DBG & 2) && v != 1.2345e300) return;
                     st_stream(reinterpret_cast<double *>(Jp + (size_t)stride8 * (unsigned)slot), v);
                 });
             } else {
@@ -331,6 +332,27 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
     int *costseg_s = segoff_s + segtot; /* the cost as a chain: one run {0, nbps}, offset 0 */
     int *par_s = costseg_s + 4;         /* [nC+1][9] chain description per column, see below */
     int *cols_s = par_s + (nC + 1) * 9; /* [nC+1] the schedule's column list */
+    /* fused multi-GPU gather (HOT && PEERS): a tile's (objective, violation) pairs are collected in
+     * shared memory and pushed ONCE, as one 16-byte store per problem and table from consecutive
+     * lanes, while the next tile's phase A runs -- not as scattered 8-byte stores from inside the
+     * latency-bound quadrature phase */
+    constexpr bool PUSH = HOT && PEERS;
+    double *res_s = smem + L.res_off();
+    double2 **peer_s = reinterpret_cast<double2 **>(
+        reinterpret_cast<char *>(smem + L.seg_off()) + ((2 * (size_t)segtot + 4 + (size_t)(nC + 1) * 10 + 1) & ~(size_t)1) * 4);
+    if constexpr (PUSH) {
+        if ((int)threadIdx.x < A.npeers) peer_s[threadIdx.x] = reinterpret_cast<double2 *>(A.peer_result[threadIdx.x]);
+    }
+    auto push_results = [&](int p0_done) {
+        if ((int)threadIdx.x < GR) {
+            const int pq = p0_done + (int)threadIdx.x;
+            if (pq < P) {
+                const double2 v = *reinterpret_cast<const double2 *>(res_s + 2 * threadIdx.x);
+                if (A.result != nullptr) reinterpret_cast<double2 *>(A.result)[pq] = v;
+                for (int r = 0; r < A.npeers; r++) peer_s[r][(size_t)A.peer_row0 + pq] = v;
+            }
+        }
+    };
 
     const int mode_obj = HOT ? 2 : A.mode_obj, mode_con = HOT ? 2 : A.mode_con;
     const bool obj_on = mode_obj >= 0 && mode_obj <= 2;
@@ -475,6 +497,9 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
         cp_async_wait_all();
         __syncthreads(); /* coefficients of this tile landed; phase B of the previous tile is done */
         if (tile + (int)gridDim.x < ntiles) stage_C(tile + gridDim.x, buf ^ 1);
+        if constexpr (PUSH) {
+            if (tile != (int)blockIdx.x) push_results(p0 - (int)gridDim.x * GR); /* the previous tile's pairs */
+        }
 
         /* ---------------- phase A: this thread's breakpoint, R problems ---------------- */
         if (active) {
@@ -620,7 +645,6 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                             double *Dp = D_s + (size_t)plr * pitch + bp;
                             const int slot_pitch = GR * pitch;
                             cost_band<PK, FULL, PK::sp_ucf()>(T, Bt, df, [&](auto, auto, double v) {
-                                if ((NTG_DBG & 4) && v != 1.2345e300) return;
                                 *Dp = v;
                                 Dp += slot_pitch;
                             });
@@ -668,7 +692,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
         /* ------- phase B: one trapezoid chain per (problem, column); the scalar cost is column nC.
          * Thread = (slot, problem lane); a slot walks the columns the schedule gave it, so that all
          * slots carry the same number of terms and a warp's lanes run the same columns. ------- */
-        for (int plr = laneB; plr < GR && !(NTG_DBG & 1); plr += lanesB) {
+        for (int plr = laneB; plr < GR; plr += lanesB) {
             const int pb = p0 + plr;
             if (pb >= P) break;
             for (int idx = it0; idx < it1; idx += istep) {
@@ -679,13 +703,12 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                 const int *ss = segstart_s + pp[3], *so = segstart_s + pp[8];
                 const double *Dj = D_s + pp[4] + (size_t)plr * pitch; /* row of band slot k: Dj + k*GR*pitch */
                 const unsigned order = (unsigned)pp[5];
-                bool run_chain = i0 < nend;
+                const bool run_chain = i0 < nend;
                 const double gI = (ipk & 0xffff) ? DI_s[plr * S + (ipk & 0xffff) - 1] : 0.0;
                 const double gF = (ipk >> 16) ? DF_s[plr * S + (ipk >> 16) - 1] : 0.0;
                 /* IntegrateVector / IntegrateFMatrixCols TRAPEZOID (src/integrator.c:21-24, :44-48 on
                  * the matrix of src/cost.c:118-132): ascending breakpoint, run by run */
                 double gU = 0.0;
-                if (NTG_DBG & 16) run_chain = false;
                 if (run_chain) {
                     const int rowp = GR * pitch;
                     int s = s0;
@@ -726,13 +749,14 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                         gU = (acc[0] + acc[1]) + (acc[2] + acc[3]);
                     }
                 }
-                if ((NTG_DBG & 8) && gU != 1.2345e300) continue;
                 if (c < nC) {
                     st_stream(A.g + (size_t)pb * nC + c, (gI + gU) + gF); /* Vector3Add, src/ntg.c:329 */
                 } else {
                     const double y = (cI_s[plr] + gU) + cF_s[plr]; /* y = I + In + F, src/ntg.c:303,328 */
                     if (HOT || (obj_v && A.f != nullptr)) A.f[pb] = y;
-                    if constexpr (!PEERS) {
+                    if constexpr (PUSH) {
+                        res_s[2 * plr] = y;
+                    } else if constexpr (!PEERS) {
                         if (A.result != nullptr) {
                             A.result[2 * (size_t)pb] = obj_v ? y : 0.0;
                             if (!con_v) A.result[2 * (size_t)pb + 1] = 0.0;
@@ -747,7 +771,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
         /* maximum constraint violation per problem: eight lanes per problem, then three shuffles.
          * Handed out from the END of the block: with fewer chains than threads these are warps that
          * have no chain to walk, so the two passes run side by side. */
-        if (con_v && (PEERS ? want_result(A) : A.result != nullptr)) {
+        if (con_v && (PUSH || (PEERS ? want_result(A) : A.result != nullptr))) {
             /* 8 lanes per problem when they fit beside the chains, else 4 (never fewer: the loop
              * below covers any size) */
             const int chain_threads = (nC + 1) * GR;
@@ -772,7 +796,8 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                 vm = fmax(vm, __shfl_xor_sync(0xffffffffu, vm, 2));
                 if (LV == 8) vm = fmax(vm, __shfl_xor_sync(0xffffffffu, vm, 4));
                 if (q < nv && part == 0 && p0 + plr < P) {
-                    if constexpr (!PEERS) A.result[2 * (size_t)(p0 + plr) + 1] = vm;
+                    if constexpr (PUSH) res_s[2 * plr + 1] = vm;
+                    else if constexpr (!PEERS) A.result[2 * (size_t)(p0 + plr) + 1] = vm;
                     else put_result(A, (size_t)(p0 + plr), 1, vm);
                 }
             }
@@ -780,6 +805,11 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
         /* the barrier at the top of the next iteration separates this phase B from the next phase A */
     }
     cp_async_wait_all();
+    if constexpr (PUSH) { /* the last tile's pairs */
+        const int nmine = ntiles > (int)blockIdx.x ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+        __syncthreads();
+        if (nmine > 0) push_results(((int)blockIdx.x + (nmine - 1) * (int)gridDim.x) * GR);
+    }
 }
 
 /* does this problem fit the register-table kernel? */
@@ -828,7 +858,8 @@ int launch_eval_small(const ntgb_launch *L)
                      a.f != nullptr && a.g != nullptr && a.c != nullptr && a.Z == nullptr && T.ncnln > 0;
     /* the steady-state kernel exists with and without the peer stores of the fused multi-GPU
      * gather, so that the single-GPU instantiation carries none of their code */
-    auto kern = full ? (hot ? (a.npeers > 0 ? ntg_eval_small_kernel<PK, true, true, true>
+    static const bool force_peers = getenv("NTG_B200_FORCE_PEERS_KERNEL") != nullptr; /* A/B: code shape vs NVLink */
+    auto kern = full ? (hot ? (a.npeers > 0 || force_peers ? ntg_eval_small_kernel<PK, true, true, true>
                                              : ntg_eval_small_kernel<PK, true, true, false>)
                             : ntg_eval_small_kernel<PK, true, false, true>)
                      : ntg_eval_small_kernel<PK, false, false, true>;

@@ -5,7 +5,7 @@
  * NPfunobj / NPfuncon (src/ntg.c:274-371).  It is written band-only (no dense
  * nbps x nC or (nbps*nnltc) x nZ scratch matrices) but performs every floating
  * point operation the reference performs, in the reference's order, so its
- * results are bit-identical to the reference's -- tests/test_oracle_vs_ref.py
+ * results are bit-identical to the reference's -- tests/test_oracle_golden.py
  * checks exactly that against oracle/_ref (the unmodified reference sources)
  * and against the committed fixtures under tests/golden/ generated from it.
  *

@@ -172,7 +172,14 @@ def run_reference_example(name: str, X: np.ndarray, mode_obj: int = 2, mode_con:
     ex = C.CDLL(os.path.join(HERE, "_ref", f"libref_{name}.so"))
     ref = C.CDLL(REF_SO)
     main = C.cast(getattr(ex, f"ref_{name}_main"), C.c_void_p).value
-    return _run_main(ref, main, X, mode_obj, mode_con)
+    import tempfile
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as td:   # examples/vanderpol.c:192 writes ./coef1
+        os.chdir(td)
+        try:
+            return _run_main(ref, main, X, mode_obj, mode_con)
+        finally:
+            os.chdir(cwd)
 
 
 def run_product_main(main_ptr: int, X: np.ndarray, mode_obj: int = 2, mode_con: int = 2, ncnln: int = 0):

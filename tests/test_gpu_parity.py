@@ -577,6 +577,13 @@ def test_eval_host_small_calls_like_npsol(torch_cuda, port, monkeypatch):
         assert_bitexact(ho["f"], o["f"][idx], f"step {step}: funobj f")
         h = pb.eval_host(X[idx], mode_obj=2, mode_con=2, jac=jac, want_Z=(step == 3))  # funobj + funcon
         check(h, idx, jac, f"step {step}")
+    # J without Z, then Z WITHOUT J (Z is carved where that J region started), then J again: the
+    # out-of-band zeros of the third call must not be the second call's flat outputs
+    for jac in (JAC_DENSE, JAC_BAND):
+        check(pb.eval_host(X[0:1], jac=jac), slice(0, 1), jac, "J, no Z")
+        hz = pb.eval_host(X[0:1], jac=JAC_NONE, want_Z=True)
+        assert np.abs(hz["Z"]).max() > 0
+        check(pb.eval_host(X[0:1], jac=jac), slice(0, 1), jac, "J again after a Z-only call")
     # the copying path gives the same bits
     monkeypatch.setenv("NTG_B200_NO_ZEROCOPY", "1")
     h2 = pb.eval_host(X[0:1], jac=JAC_DENSE)

@@ -308,7 +308,7 @@ __device__ __forceinline__ void cost_band(const ntgb_devtab &T, const double *Bt
  * in band layout, f / g / c / J all requested, Z not requested. */
 template <class PK, bool FULL, bool HOT = false, bool PEERS = true>
 __global__ void __launch_bounds__(256, 2)
-ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R, int segtot)
+ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R, int segtot, int pdl)
 {
     constexpr int NOUT = PK::kNout;
     constexpr int NZ = pk_nz<PK>();
@@ -382,7 +382,13 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
         cp_async_commit();
     };
     int buf = 0;
-    if ((int)blockIdx.x < ntiles) stage_C(blockIdx.x, 0);
+    /* pdl: launched with programmatic stream serialization -- this grid may start while the grid in
+     * front of it in the stream is still running.  Everything up to griddepcontrol.wait only reads
+     * the batch-shared tables (written once at create time), so the whole prologue overlaps the
+     * previous launch; coefficients are read and results written after the wait.  The grid behind
+     * this one may start its own prologue as soon as every CTA of this grid is resident. */
+    if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    else if ((int)blockIdx.x < ntiles) stage_C(blockIdx.x, 0);
 
     /* ---- once per CTA: dt, offset runs, accumulators; once per thread: its table slice ---- */
     for (int n = threadIdx.x; n < pitch + 2; n += blockDim.x) {
@@ -490,7 +496,10 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
         }
         cols_s[c] = use_sched ? __ldg(sched_cols + c) : c;
     }
-
+    if (pdl) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if ((int)blockIdx.x < ntiles) stage_C(blockIdx.x, 0);
+    }
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
         const int p0 = tile * GR;
@@ -874,7 +883,18 @@ int launch_eval_small(const ntgb_launch *L)
     cfg.blockDim = dim3((unsigned)block);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = (cudaStream_t)L->args.stream;
-    const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, T, L->args, G, R, segtot);
+    /* programmatic dependent launch: the prologue (tables into registers / shared memory) runs while
+     * the kernel in front of this one in the stream drains; NTG_B200_NO_PDL=1 turns it off */
+    static const bool no_pdl = getenv("NTG_B200_NO_PDL") != nullptr;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    const int pdl = no_pdl ? 0 : 1;
+    if (pdl) {
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, T, L->args, G, R, segtot, pdl);
     if (le != cudaSuccess && getenv("NTG_B200_DEBUG"))
         fprintf(stderr, "K1s launch failed: grid %d block %d smem %zu G %d R %d P %d nb %d: %s\n", grid, block, smem, G,
                 R, P, nb, cudaGetErrorString(le));

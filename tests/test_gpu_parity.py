@@ -7,6 +7,8 @@ pattern bit-exact; flat outputs, cost, gradient, constraints, Jacobian within
 The "exact" pack variant (-fmad=false, reference summation order) is held to
 the stronger bar of bit-identity wherever no libm call is involved.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -592,3 +594,19 @@ def test_eval_host_small_calls_like_npsol(torch_cuda, port, monkeypatch):
     for k in ("f", "g", "c", "J"):
         assert_bitexact(h1[k], h2[k], f"staging block vs copies: {k}")
     pb.close()
+
+
+def test_fused_peer_gather_matches_nccl_all_gather(torch_cuda):
+    """Two ranks (one per GPU, torchrun): the gathered (objective, violation) tables the evaluators
+    write with peer stores equal an NCCL all_gather bit for bit -- K1s steady state and values-only,
+    a ragged shard, K1c.  Needs two GPUs with peer access; skipped on a one-GPU box."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    tool = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "peer_gather_check.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29731", tool],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "PEER GATHER OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

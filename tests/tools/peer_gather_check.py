@@ -34,6 +34,22 @@ for cfg, Ptot in (("cfg4", 8192 * world), ("cfg2", 1000 * world + 3), ("cfg5", 8
     if rank == 0:
         print(f"{cfg}: P_total {Ptot}, {world} ranks: fused gather == NCCL all_gather on every rank: {bool(allok.item())}", flush=True)
     assert ok, f"rank {rank}: {cfg} tables differ"
+    if cfg == "cfg4":
+        # the other launch shapes: values only (mode 0, no Jacobian) goes through the general
+        # result path of the same kernel; a second steady-state launch overwrites the tables
+        pg.table().zero_()
+        pg.fence()
+        out0 = pb.alloc_outputs(hi - lo, JAC_BAND)
+        a0 = pb.eval_args(X, out0, 0, 0, JAC_BAND, 0, st, peers=pg)
+        pb.launch(a0)
+        pg.fence()
+        want0 = gather_results(out0["result"], Ptot)
+        ok0 = torch.equal(pg.table(), want0) and torch.equal(want0[:, 0], want[:, 0])
+        f0 = torch.tensor([1 if ok0 else 0], device="cuda")
+        dist.all_reduce(f0, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print(f"{cfg}: values-only launch (mode 0): fused gather == NCCL all_gather: {bool(f0.item())}", flush=True)
+        assert ok0, f"rank {rank}: {cfg} mode-0 tables differ"
     pg.close()
     pb.close()
 if rank == 0:

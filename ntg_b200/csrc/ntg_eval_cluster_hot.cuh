@@ -188,8 +188,12 @@ __device__ __forceinline__ void band_one_output(const double *Bt, const double *
 
 template <class PK, bool PEERS>
 __global__ void __launch_bounds__(256, 1)
-ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int cwin, int plan_smem, int NST, int plan_share)
+ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int cwin, int plan_smem, int NST, int plan_share,
+                            int pdl)
 {
+    /* programmatic dependent launch (see ntg_eval_small.cuh): everything up to griddepcontrol.wait reads
+     * batch-shared tables only and overlaps the grid in front of this one in the stream */
+    if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     constexpr int NOUT = PK::kNout;
     constexpr int NZ = pk_nz<PK>();
     constexpr int MD0 = PK::md(0);
@@ -327,11 +331,18 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int cwi
     auto tile_base = [&](int p) { return ((size_t)p * T.ncnln + T.nnlic) * S + (size_t)rank * T.nnltc * S * bpc; };
     const unsigned n_st = (unsigned)(JPS * ORD * cnt);
 
+    if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory"); /* coefficients are read and results written from here on */
+
     if (service) {
         /* =================== the service warp: drain stages, finish the scalar cost =================== */
         unsigned st = 0, ph = 0;
         int prev_st = -1;
         int buf = 0;
+        double res_y = 0.0, res_v = 0.0;
+        double2 *my_peer = nullptr;
+        if constexpr (PEERS) {
+            if (rank == 0 && lane < A.npeers) my_peer = reinterpret_cast<double2 *>(A.peer_result[lane]);
+        }
         unsigned use = 0; /* how often buffer `buf` has been used before: use = (iteration / 2) */
         int it = 0;
         const unsigned stage_flip = n_st & 1u; /* does the parity of a stage's first element flip from stage to stage? */
@@ -407,13 +418,18 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int cwi
                     }
                     const double y = (sc_s[buf * 2 + 0] + In) + sc_s[buf * 2 + 1]; /* y = I + In + F, src/ntg.c:328 */
                     A.f[p] = y;
-                    if (want_result<PEERS>(A)) {
-                        put_result<PEERS>(A, (size_t)p, 0, y);
-                        put_result<PEERS>(A, (size_t)p, 1, __longlong_as_double((long long)vb));
-                    }
+                    res_y = y;
+                    res_v = __longlong_as_double((long long)vb);
+                    if (A.result != nullptr) reinterpret_cast<double2 *>(A.result)[p] = make_double2(res_y, res_v);
                     for (int r = 1; r < CL; r++) mbar_arrive_remote_relaxed(map_to_rank(free_a + 8u * (unsigned)buf, r));
                 }
                 __syncwarp();
+                if constexpr (PEERS) {
+                    /* fused multi-GPU gather: lane r stores the pair into rank r's table -- one 16-byte
+                     * peer store per table, all tables at once, pointers fetched once per launch */
+                    const double yy = __shfl_sync(0xffffffffu, res_y, 0), vv = __shfl_sync(0xffffffffu, res_v, 0);
+                    if (my_peer != nullptr) my_peer[(size_t)A.peer_row0 + p] = make_double2(yy, vv);
+                }
             }
         }
         bulk_wait_all();
@@ -721,7 +737,7 @@ int launch_eval_cluster_hot(const ntgb_launch *L)
         if (!devtab_one_table(T) || T.plan == nullptr || T.plan_halo < 0) return -1001;
         const bool hot = a.mode_obj == 2 && a.mode_con == 2 && a.jac_layout == NTGB_JAC_BAND && a.J != nullptr &&
                          a.f != nullptr && a.g != nullptr && a.c != nullptr && a.Z == nullptr && T.nnltc == PK::kNnltc &&
-                         ((uintptr_t)a.J & 15u) == 0;
+                         ((uintptr_t)a.J & 15u) == 0 && ((uintptr_t)a.result & 15u) == 0; /* 16-byte bulk copies / pair stores */
         if (!hot) return -1001;
         for (int j = 0; j < T.nout; j++)
             if (T.order[j] != PK::kMaxOrd) return -1001;
@@ -751,7 +767,8 @@ int launch_eval_cluster_hot(const ntgb_launch *L)
         }
         const size_t smem = lay.bytes();
         if (smem > (size_t)L->max_smem_optin) return -1001;
-        auto kern = a.npeers > 0 ? ntg_eval_cluster_hot_kernel<PK, true> : ntg_eval_cluster_hot_kernel<PK, false>;
+        static const bool force_peers = getenv("NTG_B200_FORCE_PEERS_KERNEL") != nullptr; /* A/B: code shape vs NVLink */
+        auto kern = (a.npeers > 0 || force_peers) ? ntg_eval_cluster_hot_kernel<PK, true> : ntg_eval_cluster_hot_kernel<PK, false>;
         cudaError_t e = raise_smem_limit((const void *)kern, L->max_smem_optin);
         if (e != cudaSuccess) return (int)e;
         int nclusters = L->sm_count / CL;
@@ -762,14 +779,18 @@ int launch_eval_cluster_hot(const ntgb_launch *L)
         cfg.blockDim = dim3((unsigned)block);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = (cudaStream_t)a.stream;
-        cudaLaunchAttribute attr[1];
+        static const bool no_pdl = getenv("NTG_B200_NO_PDL") != nullptr;
+        const int pdl = no_pdl ? 0 : 1;
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = (unsigned)CL;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        return (int)cudaLaunchKernelEx(&cfg, kern, T, a, T.plan_cwin, plan_smem, lay.nst, plan_share);
+        cfg.numAttrs = pdl ? 2 : 1;
+        return (int)cudaLaunchKernelEx(&cfg, kern, T, a, T.plan_cwin, plan_smem, lay.nst, plan_share, pdl);
     }
 }
 

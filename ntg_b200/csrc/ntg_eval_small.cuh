@@ -75,7 +75,7 @@ struct SmallSmem {
     {
         /* ints: run tables, cost run, chain table, column list; then (8-byte aligned) the peer table pointers */
         const size_t ints = 2 * (size_t)segtot + 4 + (size_t)(nC + 1) * 10;
-        return seg_off() * 8 + ((ints + 1) & ~(size_t)1) * 4 + NTGB_MAXPEERS * 8 + 8;
+        return seg_off() * 8 + ((ints + 1) & ~(size_t)1) * 4 + (NTGB_MAXPEERS + 1) * 8 + 8;
     }
 };
 
@@ -304,6 +304,20 @@ __device__ __forceinline__ void cost_band(const ntgb_devtab &T, const double *Bt
     else band_from_regs<PK, FULL, false, kDense>(T, Bt, df, sink);
 }
 
+/* Fused multi-GPU gather: thread q stores the (objective, violation) pair of problem p0 + q of a
+ * finished tile -- collected in shared memory by phase B -- into every destination table (the local
+ * one and every rank's gathered table), one 16-byte store each.  The evaluator is bound by
+ * instruction issue (ncu: every instruction per warp and tile is worth ~0.07 % of the launch), so
+ * this is a call that a few threads of one warp make once per tile, NOT inlined: its addresses and
+ * loop stay out of the main loop's register allocation.  (Tried and dropped: pushing from the local
+ * global table instead of shared memory -- the load queues behind the SM's store stream and holds
+ * the tile's barrier: 129 us per step at 2 GPUs instead of 125.) */
+__device__ __noinline__ void push_pairs(const double *res_s, double2 *const *dst_s, int ndst, int pq)
+{
+    const double2 v = *reinterpret_cast<const double2 *>(res_s + 2 * threadIdx.x);
+    for (int r = 0; r < ndst; r++) dst_s[r][pq] = v;
+}
+
 /* HOT = the solver's steady state, known at compile time: funobj mode 2 + funcon mode 2, Jacobian
  * in band layout, f / g / c / J all requested, Z not requested. */
 template <class PK, bool FULL, bool HOT = false, bool PEERS = true>
@@ -338,21 +352,14 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
      * latency-bound quadrature phase */
     constexpr bool PUSH = HOT && PEERS;
     double *res_s = smem + L.res_off();
-    double2 **peer_s = reinterpret_cast<double2 **>(
+    double2 **dst_s = reinterpret_cast<double2 **>(
         reinterpret_cast<char *>(smem + L.seg_off()) + ((2 * (size_t)segtot + 4 + (size_t)(nC + 1) * 10 + 1) & ~(size_t)1) * 4);
-    if constexpr (PUSH) {
-        if ((int)threadIdx.x < A.npeers) peer_s[threadIdx.x] = reinterpret_cast<double2 *>(A.peer_result[threadIdx.x]);
+    const int ndst = PUSH ? A.npeers + (A.result != nullptr ? 1 : 0) : 0;
+    if constexpr (PUSH) { /* destination tables: [local,] rank 0, rank 1, ... offset to this rank's first row */
+        const int t = (int)threadIdx.x, loc = A.result != nullptr ? 1 : 0;
+        if (t == 0 && loc) dst_s[0] = reinterpret_cast<double2 *>(A.result);
+        if (t < A.npeers) dst_s[loc + t] = reinterpret_cast<double2 *>(A.peer_result[t]) + A.peer_row0;
     }
-    auto push_results = [&](int p0_done) {
-        if ((int)threadIdx.x < GR) {
-            const int pq = p0_done + (int)threadIdx.x;
-            if (pq < P) {
-                const double2 v = *reinterpret_cast<const double2 *>(res_s + 2 * threadIdx.x);
-                if (A.result != nullptr) reinterpret_cast<double2 *>(A.result)[pq] = v;
-                for (int r = 0; r < A.npeers; r++) peer_s[r][(size_t)A.peer_row0 + pq] = v;
-            }
-        }
-    };
 
     const int mode_obj = HOT ? 2 : A.mode_obj, mode_con = HOT ? 2 : A.mode_con;
     const bool obj_on = mode_obj >= 0 && mode_obj <= 2;
@@ -390,28 +397,11 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
     if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     else if ((int)blockIdx.x < ntiles) stage_C(blockIdx.x, 0);
 
-    /* ---- once per CTA: dt, offset runs, accumulators; once per thread: its table slice ---- */
-    for (int n = threadIdx.x; n < pitch + 2; n += blockDim.x) {
-        const double lo = (n >= 1 && n < nbps) ? (__ldg(T.bps + n) - __ldg(T.bps + n - 1)) * 0.5 : 0.0;
-        const double hi = (n + 1 < nbps) ? (__ldg(T.bps + n + 1) - __ldg(T.bps + n)) * 0.5 : 0.0;
-        wt_s[n] = (n >= 1 && n < nbps) ? __ldg(T.bps + n) - __ldg(T.bps + n - 1) : 0.0;
-        Wf_s[n] = lo + hi;
-    }
-    {
-        int base = 0;
-        for (int j = 0; j < T.nout; j++) {
-            for (int i = threadIdx.x; i <= T.nseg[j]; i += blockDim.x) {
-                segstart_s[base + i] = __ldg(T.seg_start[j] + i);
-                segoff_s[base + i] = __ldg(T.seg_off[j] + i);
-            }
-            base += T.nseg[j] + 1;
-        }
-    }
-    for (int q = threadIdx.x; q < GR; q += blockDim.x) {
-        cI_s[q] = 0.0;
-        cF_s[q] = 0.0;
-    }
-
+    /* ---- once per CTA: dt, offset runs, accumulators; once per thread: its table slice ----
+     * A thread's table slice is requested FIRST (it is only consumed in phase A), and the three
+     * table-building loops below start at different warps of the CTA (tw / ts / tc): their global
+     * loads are independent of each other, so the prologue costs about one load round trip instead
+     * of one per loop (measured with device time stamps: 1.9 - 2.5 us before). */
     const int pl = threadIdx.x / nbps;
     const int bp = threadIdx.x - pl * nbps;
     const bool active = pl < G;
@@ -430,6 +420,31 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
             for (int d = 0; d < MD; d++)
                 Bt[TB + k * MD + d] = (active && k < order) ? __ldg(T.Bt[j] + (size_t)(k * MD + d) * nbps + bp) : 0.0;
     });
+    const int bdim = (int)blockDim.x;
+    auto rot = [&](int off) { const int t = (int)threadIdx.x - off; return t < 0 ? t + bdim : t; };
+    const int tw = (int)threadIdx.x;                                   /* weights: from warp 0      */
+    const int ts = rot(bdim >= 128 ? 96 : 0);                          /* run tables: from warp 3   */
+    const int tc = rot(bdim >= 256 ? 128 : (bdim >= 128 ? 64 : 0));    /* chain table: from warp 4  */
+    for (int n = tw; n < pitch + 2; n += bdim) {
+        const double lo = (n >= 1 && n < nbps) ? (__ldg(T.bps + n) - __ldg(T.bps + n - 1)) * 0.5 : 0.0;
+        const double hi = (n + 1 < nbps) ? (__ldg(T.bps + n + 1) - __ldg(T.bps + n)) * 0.5 : 0.0;
+        wt_s[n] = (n >= 1 && n < nbps) ? __ldg(T.bps + n) - __ldg(T.bps + n - 1) : 0.0;
+        Wf_s[n] = lo + hi;
+    }
+    {
+        int base = 0;
+        for (int j = 0; j < T.nout; j++) {
+            for (int i = ts; i <= T.nseg[j]; i += bdim) {
+                segstart_s[base + i] = __ldg(T.seg_start[j] + i);
+                segoff_s[base + i] = __ldg(T.seg_off[j] + i);
+            }
+            base += T.nseg[j] + 1;
+        }
+    }
+    for (int q = threadIdx.x; q < GR; q += blockDim.x) {
+        cI_s[q] = 0.0;
+        cF_s[q] = 0.0;
+    }
 
     /* phase-B mapping (tile-invariant): slot and problem lane of this thread, its column list */
     const bool want_g = HOT || (obj_d && A.g != nullptr);
@@ -459,7 +474,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
      * [0] first breakpoint i0, [1] last term nend (no chain when i0 >= nend), [2] run holding i0,
      * [3]/[8] where the output's run starts / run offsets sit in segstart_s, [4] the column's base
      * inside D_s (doubles), [5] band width, [6] local column, [7] (slot in DI)+1 | ((slot in DF)+1)<<16 */
-    for (int c = threadIdx.x; c <= nC; c += blockDim.x) {
+    for (int c = tc; c <= nC; c += bdim) {
         int *pp = par_s + c * 9;
         if (c == nC) {
             pp[0] = 0; pp[1] = (doU && obj_v) ? nbps - 1 : 0; pp[2] = 0; pp[3] = 2 * segtot; pp[8] = 2 * segtot + 2;
@@ -506,8 +521,9 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
         cp_async_wait_all();
         __syncthreads(); /* coefficients of this tile landed; phase B of the previous tile is done */
         if (tile + (int)gridDim.x < ntiles) stage_C(tile + gridDim.x, buf ^ 1);
-        if constexpr (PUSH) {
-            if (tile != (int)blockIdx.x) push_results(p0 - (int)gridDim.x * GR); /* the previous tile's pairs */
+        if constexpr (PUSH) { /* the previous tile's pairs (phase B of that tile ended at the barrier above) */
+            const int pq = p0 - (int)gridDim.x * GR + (int)threadIdx.x;
+            if ((int)threadIdx.x < GR && tile != (int)blockIdx.x && pq < P) push_pairs(res_s, dst_s, ndst, pq);
         }
 
         /* ---------------- phase A: this thread's breakpoint, R problems ---------------- */
@@ -817,7 +833,8 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
     if constexpr (PUSH) { /* the last tile's pairs */
         const int nmine = ntiles > (int)blockIdx.x ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
         __syncthreads();
-        if (nmine > 0) push_results(((int)blockIdx.x + (nmine - 1) * (int)gridDim.x) * GR);
+        const int pq = ((int)blockIdx.x + (nmine - 1) * (int)gridDim.x) * GR + (int)threadIdx.x;
+        if (nmine > 0 && (int)threadIdx.x < GR && pq < P) push_pairs(res_s, dst_s, ndst, pq);
     }
 }
 
@@ -864,11 +881,13 @@ int launch_eval_small(const ntgb_launch *L)
     if (smem > (size_t)L->max_smem_optin) return -1001;
     const ntgb_eval_args &a = L->args;
     const bool hot = a.mode_obj == 2 && a.mode_con == 2 && a.jac_layout == NTGB_JAC_BAND && a.J != nullptr &&
-                     a.f != nullptr && a.g != nullptr && a.c != nullptr && a.Z == nullptr && T.ncnln > 0;
+                     a.f != nullptr && a.g != nullptr && a.c != nullptr && a.Z == nullptr && T.ncnln > 0 &&
+                     ((uintptr_t)a.result & 15u) == 0; /* the peer-store variant writes (objective, violation) as one 16-byte pair */
     /* the steady-state kernel exists with and without the peer stores of the fused multi-GPU
      * gather, so that the single-GPU instantiation carries none of their code */
     static const bool force_peers = getenv("NTG_B200_FORCE_PEERS_KERNEL") != nullptr; /* A/B: code shape vs NVLink */
-    auto kern = full ? (hot ? (a.npeers > 0 || force_peers ? ntg_eval_small_kernel<PK, true, true, true>
+    const bool push_ok = G * R <= block; /* one thread per pair of a tile */
+    auto kern = full ? (hot && (a.npeers == 0 || push_ok) ? ((a.npeers > 0 || force_peers) && push_ok ? ntg_eval_small_kernel<PK, true, true, true>
                                              : ntg_eval_small_kernel<PK, true, true, false>)
                             : ntg_eval_small_kernel<PK, true, false, true>)
                      : ntg_eval_small_kernel<PK, false, false, true>;

@@ -10,6 +10,7 @@ ap.add_argument("--variants", default="exact,fast")
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--p5", type=int, default=4096)
 ap.add_argument("--dense", action="store_true")
+ap.add_argument("--graph", action="store_true", help="time ONE CUDA graph of --iters launches (what bench.py does)")
 ap.add_argument("--mode_obj", type=int, default=2)
 ap.add_argument("--mode_con", type=int, default=2)
 a = ap.parse_args()
@@ -31,9 +32,19 @@ for cfg in a.cfgs.split(","):
         for i in range(3): pb.launch(args[i % nset])
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(a.iters): pb.launch(args[i % nset])
-        e1.record(); torch.cuda.synchronize()
+        if a.graph:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                cs = torch.cuda.current_stream().cuda_stream
+                for i in range(a.iters):
+                    x, o = sets[i % nset]
+                    pb.launch(pb.eval_args(x, o, a.mode_obj, a.mode_con, jac, 0, cs))
+            g.replay(); torch.cuda.synchronize()
+            e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+        else:
+            e0.record()
+            for i in range(a.iters): pb.launch(args[i % nset])
+            e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / a.iters
         gbs = P * bytes_eval / (ms * 1e-3) / 1e9
         print(f"{cfg} {var:5s} P={P} {'dense' if a.dense else 'band'} sets={nset} {ms*1e3:9.1f} us/launch  "

@@ -9,6 +9,7 @@ ap.add_argument("--cfgs", default="cfg2,cfg3,cfg4,cfg5")
 ap.add_argument("--variants", default="exact,fast")
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--p5", type=int, default=4096)
+ap.add_argument("--p4", type=int, default=0, help="problems for cfg4 (default: the config's 65536)")
 ap.add_argument("--dense", action="store_true")
 ap.add_argument("--graph", action="store_true", help="time ONE CUDA graph of --iters launches (what bench.py does)")
 ap.add_argument("--mode_obj", type=int, default=2)
@@ -19,6 +20,7 @@ L2 = 126e6
 for cfg in a.cfgs.split(","):
     spec, P = configs.get(cfg)
     if cfg == "cfg5": P = a.p5
+    if cfg == "cfg4" and a.p4: P = a.p4
     X = torch.from_numpy(configs.coefficients(cfg, P, spec)).cuda()
     for var in a.variants.split(","):
         pb = Problem(spec, 0, fast=(var == "fast"))

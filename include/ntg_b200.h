@@ -303,6 +303,32 @@ typedef struct ntgb_nlp_opts {
 int  ntgb_solve_nlp(ntgb_problem *pb, int P, double *C, double *f, double *viol, int *iters, int *status,
                     const ntgb_nlp_opts *opts, void *stream);
 
+/*
+ * Batched SQP solver: what NPSOL does for the reference (/root/reference/src/ntg.c:250-253), for P
+ * problems at once.  Linear equality rows are eliminated (C = C_part + N y); per iteration ONE
+ * batched evaluation (cost, gradient, constraints, band Jacobian), then one CTA per problem solves
+ * the dense QP subproblem on the reduced space in shared memory (Goldfarb-Idnani dual active set;
+ * a Gauss-Newton step on the violated rows when the linearised rows are inconsistent), damped BFGS
+ * on the reduced Lagrangian, Armijo search on the L1 merit (two batched values-only evaluations).
+ * Outputs as NPSOL's (/root/reference/src/ntg.h:64-68): lambda / istate over the general
+ * constraints in NPSOL's order [nclin linear rows ; ncnln nonlinear rows] (lambda > 0 at a lower
+ * bound, < 0 at an upper one; istate 0 inactive, 1 lower, 2 upper, 3 equality); either may be NULL.
+ * status: 1 converged (violation <= ctol, reduced Lagrangian gradient <= gtol*max(1,|f|)), 2 no
+ * decrease of the merit function even from B = I, 4 stationary point of the violation (locally
+ * infeasible), 0 iteration limit.  Limit: the per-problem work space (about 4 nr^2 + m nr doubles for
+ * nr free directions and m rows) must fit in shared memory -- short horizons; NTGB_ELIMIT otherwise.
+ */
+typedef struct ntgb_sqp_opts {
+    int max_iter;     /* SQP iterations, default 100 */
+    double gtol;      /* default 1e-6 */
+    double ctol;      /* default 1e-8 */
+    double rho_pen;   /* Gauss-Newton weight of inconsistent rows, relative to trace(B)/nr / max |a_i|^2; default 1e4 */
+    double c1;        /* Armijo constant, default 1e-4 */
+    int check_every;  /* host reads the done counter every this many iterations, default 4 */
+} ntgb_sqp_opts;
+int  ntgb_solve_sqp(ntgb_problem *pb, int P, double *C, double *f, double *viol, int *iters, int *status,
+                    double *lambda, int *istate, const ntgb_sqp_opts *opts, void *stream);
+
 /* Gathered result tables for the fused multi-GPU gather (ntgb_eval_args.peer_result): alloc creates
  * this rank's table (rows x 2 doubles, zeroed) and the 64-byte CUDA IPC handle the other ranks
  * need; open maps another rank's table into this process (peer access over NVLink is enabled on

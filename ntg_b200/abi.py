@@ -92,6 +92,12 @@ class NlpOpts(C.Structure):
                 ("check_every", C.c_int)]
 
 
+class SqpOpts(C.Structure):
+    """ntgb_sqp_opts (include/ntg_b200.h)"""
+    _fields_ = [("max_iter", C.c_int), ("gtol", C.c_double), ("ctol", C.c_double), ("rho_pen", C.c_double),
+                ("c1", C.c_double), ("check_every", C.c_int)]
+
+
 class NtgbPack(C.Structure):
     _fields_ = [
         ("name", C.c_char_p),

@@ -30,6 +30,7 @@
 #include "ntg_b200.h"
 #include "ntg_kernel_args.h"
 #include "pgs_device.cuh"
+#include "ntg_sqp.cuh"
 
 namespace {
 
@@ -144,10 +145,23 @@ struct ntgb_problem {
         int *li_idx = nullptr;      /* [n_li] linear row of general constraint i */
         double *hl = nullptr, *hu = nullptr; /* [m] bounds: linear inequality rows, then the nonlinear rows */
         double *A = nullptr;        /* dense nclin x nC, column-major (for A_in^T mu) */
+        std::vector<double> hN;     /* host copy of N */
+        std::vector<int> eq, li;    /* linear rows: eliminated equalities / kept as general constraints */
         size_t cap = 0, capt = 0;
         double *blob = nullptr, *tblob = nullptr;
         int *iblob = nullptr;
     } alm;
+    /* ntgb_solve_sqp: on top of alm's reduced form */
+    struct {
+        bool ready = false;
+        double *ArN = nullptr; /* [n_li][nr] */
+        double *W = nullptr;   /* [me][nC] (Ae Ae')^-1 Ae */
+        int *eq_idx = nullptr; /* [me] */
+        int me = 0;
+        size_t cap = 0;
+        double *blob = nullptr, *tblob = nullptr;
+        int *iblob = nullptr;
+    } sqp;
     /* scratch of ntgb_linesearch: trial coefficients, result table, linear violation */
     struct { size_t n = 0; double *Ct = nullptr, *res = nullptr, *lv = nullptr; } ls;
 };
@@ -798,6 +812,283 @@ void host_band_row(const ntgb_problem *pb, const double *dz, int bp, double *ban
     }
 }
 
+/* reduced form shared by ntgb_solve_nlp and ntgb_solve_sqp: linear equality rows eliminated
+ * (C = Cpart + N y), the other linear rows and the nonlinear rows kept as general constraints */
+int alm_prepare(ntgb_problem *pb)
+{
+    auto &al = pb->alm;
+    if (al.ready) return 0;
+    const ntgb_dims &dm = pb->dims;
+    const int nC = dm.nC, nclin = dm.nclin, ncnln = dm.ncnln;
+    int rc;
+    {
+        /* split the linear rows: equalities are eliminated, the rest become general constraints */
+        std::vector<int> eq, li;
+        for (int i = 0; i < nclin; i++) (pb->lin_lb[i] == pb->lin_ub[i] ? eq : li).push_back(i);
+        const int me = (int)eq.size();
+        std::vector<double> Ae((size_t)std::max(me, 1) * nC, 0.0), be((size_t)me);
+        for (int r = 0; r < me; r++) {
+            be[r] = pb->lin_lb[eq[r]];
+            for (int c = 0; c < nC; c++) Ae[r + (size_t)c * me] = pb->A[eq[r] + (size_t)c * nclin];
+        }
+        std::vector<double> N, Cpart;
+        int nr = 0;
+        if ((rc = reduce_linear(Ae, me, nC, be, N, Cpart, nr))) return rc;
+        al.nr = nr;
+        al.hN = N;
+        al.eq = eq;
+        al.li = li;
+        al.n_li = (int)li.size();
+        al.m = al.n_li + ncnln;
+        if (N.empty()) N.push_back(0.0);
+        if ((rc = dev_upload(pb, &al.N, N.data(), N.size()))) return rc;
+        if ((rc = dev_upload(pb, &al.Cpart, Cpart.data(), Cpart.size()))) return rc;
+        if (li.empty()) li.push_back(0);
+        if ((rc = dev_upload(pb, &al.li_idx, li.data(), li.size()))) return rc;
+        /* bounds of the general constraints: NPSOL's bl/bu behind the variables and, for the
+         * linear rows, the expanded linear bounds */
+        std::vector<double> bl((size_t)nC + nclin + ncnln), bu(bl.size());
+        if ((rc = ntgb_get_bounds(pb, bl.data(), bu.data()))) return rc;
+        std::vector<double> hl((size_t)std::max(al.m, 1), 0.0), hu((size_t)std::max(al.m, 1), 0.0);
+        for (int i = 0; i < al.n_li; i++) { hl[i] = pb->lin_lb[li[i]]; hu[i] = pb->lin_ub[li[i]]; }
+        for (int i = 0; i < ncnln; i++) { hl[al.n_li + i] = bl[(size_t)nC + nclin + i]; hu[al.n_li + i] = bu[(size_t)nC + nclin + i]; }
+        if ((rc = dev_upload(pb, &al.hl, hl.data(), hl.size()))) return rc;
+        if ((rc = dev_upload(pb, &al.hu, hu.data(), hu.size()))) return rc;
+        std::vector<double> Ad = pb->A;
+        if (Ad.empty()) Ad.push_back(0.0);
+        if ((rc = dev_upload(pb, &al.A, Ad.data(), Ad.size()))) return rc;
+    }
+    al.ready = true;
+    return 0;
+}
+
+/* ---- ntgb_solve_sqp: one CTA per problem runs ntg_sqp.cuh's sqp_step in shared memory ---------- */
+namespace sqp = ntgb::sqp;
+
+__global__ void k_scale_copy(long long n, double a, const double *x, double *y)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = a * x[i];
+}
+
+struct SqpDesc {
+    int nC, nr, m, n_li, nclin, ncnln;
+    const double *N;      /* [nr][nC] */
+    const double *ArN;    /* [n_li][nr] reduced gradients of the linear inequality rows */
+    const int *li_idx;    /* [n_li] */
+    const double *hl, *hu; /* [m] */
+    double gtol, ctol, rho_pen;
+};
+
+/* per-problem solver state, problem-major */
+struct SqpArrays {
+    double *y, *B, *lam, *sprev, *grLold, *d, *scal;
+    int *flag, *istate;
+};
+
+__global__ void k_sqp_init(int P, SqpDesc D, SqpArrays S, const double *Cpart, double *C, int *state, int *iters)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const int nC = D.nC, nr = D.nr;
+    double *Cp = C + (size_t)p * nC, *y = S.y + (size_t)p * nr;
+    for (int k = 0; k < nr; k++) {
+        double a = 0.0;
+        for (int e = 0; e < nC; e++) a += D.N[(size_t)k * nC + e] * (Cp[e] - Cpart[e]);
+        y[k] = a;
+    }
+    for (int e = 0; e < nC; e++) {
+        double a = Cpart[e];
+        for (int k = 0; k < nr; k++) a += D.N[(size_t)k * nC + e] * y[k];
+        Cp[e] = a;
+    }
+    for (int e = 0; e < nr * nr; e++) S.B[(size_t)p * nr * nr + e] = (e / nr == e % nr) ? 1.0 : 0.0;
+    for (int i = 0; i < D.m; i++) {
+        S.lam[(size_t)p * D.m + i] = 0.0;
+        S.istate[(size_t)p * D.m + i] = 0;
+    }
+    for (int k = 0; k < 8; k++) {
+        S.scal[(size_t)p * 8 + k] = 0.0;
+        S.flag[(size_t)p * 8 + k] = 0;
+    }
+    S.flag[(size_t)p * 8 + 3] = 1; /* B is the identity */
+    state[p] = 0;
+    iters[p] = 0;
+}
+
+/* reduced gradient, row values and reduced row gradients of problem p into shared memory, then one
+ * SQP iteration up to the search direction (ntg_sqp.cuh), then dC = N d */
+__global__ void k_sqp_step(int P, ntgb_devtab T, SqpDesc D, SqpArrays S, const double *f, const double *g, const double *c,
+                           const double *J, const double *lin, double *dC, double *phi0, double *dphi0, int *state, int *count)
+{
+    extern __shared__ double sq_smem[];
+    const int p = blockIdx.x;
+    if (p >= P) return;
+    const int nC = D.nC, nr = D.nr, m = D.m, n_li = D.n_li, nt = (int)blockDim.x, tid = (int)threadIdx.x;
+    double *dCp = dC + (size_t)p * nC;
+    if (state[p] != 0) {
+        for (int e = tid; e < nC; e += nt) dCp[e] = 0.0;
+        if (tid == 0) dphi0[p] = 0.0, phi0[p] = 0.0;
+        return;
+    }
+    sqp::Qp w;
+    double *Bm, *Lm, *vec, *gr, *hrow;
+    const size_t nd = sqp::sqp_smem_doubles(nr, m, nt);
+    sqp::sqp_carve(sq_smem, reinterpret_cast<int *>(sq_smem + nd), nr, m, nt, w, Bm, Lm, vec, gr, hrow);
+    const int ld = w.ld;
+    const double *gp = g + (size_t)p * nC;
+    for (int k = tid; k < nr; k += nt) {
+        double a = 0.0;
+        for (int e = 0; e < nC; e++) a += D.N[(size_t)k * nC + e] * gp[e];
+        gr[k] = a;
+    }
+    for (int i = tid; i < m; i += nt) {
+        double *Ai = w.A + (size_t)i * ld;
+        if (i < n_li) {
+            hrow[i] = lin[(size_t)p * D.nclin + D.li_idx[i]];
+            for (int k = 0; k < nr; k++) Ai[k] = D.ArN[(size_t)i * nr + k];
+            continue;
+        }
+        /* nonlinear row r of the band-compact Jacobian (include/ntg_b200.h): slot jk0[j] + k of
+         * output j holds the derivative with respect to coefficient iC[j] + offset + k */
+        const int r = i - n_li;
+        hrow[i] = c[(size_t)p * D.ncnln + r];
+        for (int k = 0; k < nr; k++) Ai[k] = 0.0;
+        const double *Jp = J + (size_t)p * T.ncnln * T.S;
+        int kind, mm = 0, bp = 0, rr = r; /* 0 initial (src/colloc.c:254: columns from iC_j), 1 trajectory, 2 final */
+        if (r < T.nnlic) kind = 0;
+        else if (r < T.nnlic + T.nnltc * T.nbps) {
+            kind = 1;
+            mm = (r - T.nnlic) / T.nbps;
+            bp = (r - T.nnlic) - mm * T.nbps;
+        } else {
+            kind = 2;
+            bp = T.nbps - 1;
+        }
+        for (int j = 0; j < T.nout; j++) {
+            const int ord = T.order[j], s0 = T.jk0[j];
+            const int col0 = T.iC[j] + (kind == 0 ? 0 : T.off[j][bp]);
+            for (int k = 0; k < ord; k++) {
+                const double v = kind == 1 ? Jp[ntgb_band_index(T.nnlic, T.nnltc, T.S, T.nbps, T.band_tile, mm, s0 + k, bp)]
+                                           : Jp[(size_t)rr * T.S + s0 + k];
+                if (v == 0.0) continue;
+                const double *Nc = D.N + (col0 + k);
+                for (int q = 0; q < nr; q++) Ai[q] += v * Nc[(size_t)q * nC];
+            }
+        }
+    }
+    __syncthreads();
+    const sqp::Coop cg{tid, nt, tid & 31, nt < 32 ? nt : 32};
+    const sqp::StepState st{S.y + (size_t)p * nr, S.B + (size_t)p * nr * nr, S.lam + (size_t)p * m, S.sprev + (size_t)p * nr,
+                            S.grLold + (size_t)p * nr, S.d + (size_t)p * nr, S.scal + (size_t)p * 8, S.flag + (size_t)p * 8,
+                            S.istate + (size_t)p * m};
+    const sqp::StepOpts so{D.gtol, D.ctol, D.rho_pen};
+    sqp::sqp_step(cg, w, st, so, f[p], gr, hrow, D.hl, D.hu, Bm, Lm, vec);
+    __syncthreads();
+    const int status = st.flag[5];
+    if (status != 0) {
+        for (int e = tid; e < nC; e += nt) dCp[e] = 0.0;
+        if (tid == 0) {
+            state[p] = status;
+            atomicAdd(count, 1);
+            phi0[p] = st.scal[1];
+            dphi0[p] = 0.0;
+        }
+        return;
+    }
+    for (int e = tid; e < nC; e += nt) {
+        double a = 0.0;
+        for (int k = 0; k < nr; k++) a += D.N[(size_t)k * nC + e] * w.x[k];
+        dCp[e] = a;
+    }
+    if (tid == 0) {
+        phi0[p] = st.scal[1];
+        dphi0[p] = st.scal[2];
+    }
+}
+
+/* L1 merit of trial point q (one warp each): f + nu * sum of the rows' bound violations */
+__global__ void k_sqp_merit(int Q, int nalpha, SqpDesc D, const double *scal, const double *f, const double *c,
+                            const double *lin, double *res, const int *pidx)
+{
+    const int q = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= Q) return;
+    const int p = pidx != nullptr ? pidx[q / nalpha] : q / nalpha;
+    double acc = 0.0;
+    for (int i = lane; i < D.m; i += 32) {
+        const double h = i < D.n_li ? lin[(size_t)q * D.nclin + D.li_idx[i]] : c[(size_t)q * D.ncnln + (i - D.n_li)];
+        const double lo = D.hl[i], hi = D.hu[i];
+        double v = 0.0;
+        if (lo > -sqp::kBig && lo - h > v) v = lo - h;
+        if (hi < sqp::kBig && h - hi > v) v = h - hi;
+        acc += v;
+    }
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (lane == 0) res[2 * (size_t)q] = f[q] + scal[(size_t)p * 8] * acc;
+}
+
+/* accept the step (y, C, s = alpha d) or ask for a restart from B = I; give up when that fails too */
+__global__ void k_sqp_update(int P, SqpDesc D, SqpArrays S, const double *Cpart, const double *phi0, const double *alpha_best,
+                             const double *phi_best, double *C, int *state, int *iters, int *count)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P || state[p] != 0) return;
+    const int nC = D.nC, nr = D.nr;
+    int *flag = S.flag + (size_t)p * 8;
+    iters[p] += 1;
+    if (!(phi_best[p] < phi0[p])) {
+        if (flag[3]) {
+            state[p] = 2;
+            atomicAdd(count, 1);
+        } else {
+            flag[2] = 1;
+            flag[0] = 0;
+        }
+        return;
+    }
+    const double a = alpha_best[p];
+    double *y = S.y + (size_t)p * nr, *sp = S.sprev + (size_t)p * nr;
+    const double *d = S.d + (size_t)p * nr;
+    for (int k = 0; k < nr; k++) {
+        sp[k] = a * d[k];
+        y[k] += sp[k];
+    }
+    double *Cp = C + (size_t)p * nC;
+    for (int e = 0; e < nC; e++) {
+        double v = Cpart[e];
+        for (int k = 0; k < nr; k++) v += D.N[(size_t)k * nC + e] * y[k];
+        Cp[e] = v;
+    }
+    flag[0] = 1;
+    flag[1] = flag[4];
+}
+
+/* NPSOL-order outputs: clambda / istate over [linear rows ; nonlinear rows].  The multipliers of the
+ * eliminated equality rows are the least-squares solution of Ae' le = g - A_in' l_in - J' l_nl
+ * (W = (Ae Ae')^-1 Ae, host-built); gL is that right-hand side in the full space (k_alm_grad). */
+__global__ void k_sqp_outputs(int P, SqpDesc D, SqpArrays S, int me, const int *eq_idx, const double *W, const double *gL,
+                              double *lambda, int *istate)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const int ntot = D.nclin + D.ncnln;
+    if (lambda != nullptr) {
+        double *lp = lambda + (size_t)p * ntot;
+        for (int i = 0; i < D.m; i++) lp[i < D.n_li ? D.li_idx[i] : D.nclin + (i - D.n_li)] = S.lam[(size_t)p * D.m + i];
+        for (int r = 0; r < me; r++) {
+            double a = 0.0;
+            for (int e = 0; e < D.nC; e++) a += W[(size_t)r * D.nC + e] * gL[(size_t)p * D.nC + e];
+            lp[eq_idx[r]] = a;
+        }
+    }
+    if (istate != nullptr) {
+        int *ip = istate + (size_t)p * ntot;
+        for (int i = 0; i < D.m; i++) ip[i < D.n_li ? D.li_idx[i] : D.nclin + (i - D.n_li)] = S.istate[(size_t)p * D.m + i];
+        for (int r = 0; r < me; r++) ip[eq_idx[r]] = 3;
+    }
+}
+
 } /* namespace */
 
 extern "C" {
@@ -851,6 +1142,9 @@ void ntgb_destroy(ntgb_problem *pb)
     if (pb->alm.blob) cudaFree(pb->alm.blob);
     if (pb->alm.tblob) cudaFree(pb->alm.tblob);
     if (pb->alm.iblob) cudaFree(pb->alm.iblob);
+    if (pb->sqp.blob) cudaFree(pb->sqp.blob);
+    if (pb->sqp.tblob) cudaFree(pb->sqp.tblob);
+    if (pb->sqp.iblob) cudaFree(pb->sqp.iblob);
     if (pb->red.blob) cudaFree(pb->red.blob);
     if (pb->red.iblob) cudaFree(pb->red.iblob);
     for (auto &h : pb->hs) {
@@ -1754,45 +2048,11 @@ int ntgb_solve_nlp(ntgb_problem *pb, int P, double *C, double *f, double *viol_o
     cudaStream_t st = (cudaStream_t)stream;
     const int nC = dm.nC, nclin = dm.nclin, ncnln = dm.ncnln;
     int rc;
+    if ((rc = alm_prepare(pb))) return rc;
     auto &al = pb->alm;
-    if (!al.ready) {
-        /* split the linear rows: equalities are eliminated, the rest become general constraints */
-        std::vector<int> eq, li;
-        for (int i = 0; i < nclin; i++) (pb->lin_lb[i] == pb->lin_ub[i] ? eq : li).push_back(i);
-        const int me = (int)eq.size();
-        std::vector<double> Ae((size_t)std::max(me, 1) * nC, 0.0), be((size_t)me);
-        for (int r = 0; r < me; r++) {
-            be[r] = pb->lin_lb[eq[r]];
-            for (int c = 0; c < nC; c++) Ae[r + (size_t)c * me] = pb->A[eq[r] + (size_t)c * nclin];
-        }
-        std::vector<double> N, Cpart;
-        int nr = 0;
-        if ((rc = reduce_linear(Ae, me, nC, be, N, Cpart, nr))) return rc;
-        if (nr > kSolveMaxNr)
-            return fail(NTGB_ELIMIT, "ntgb_solve_nlp: %d free directions after eliminating the linear equalities (limit %d)",
-                        nr, kSolveMaxNr);
-        al.nr = nr;
-        al.n_li = (int)li.size();
-        al.m = al.n_li + ncnln;
-        if (N.empty()) N.push_back(0.0);
-        if ((rc = dev_upload(pb, &al.N, N.data(), N.size()))) return rc;
-        if ((rc = dev_upload(pb, &al.Cpart, Cpart.data(), Cpart.size()))) return rc;
-        if (li.empty()) li.push_back(0);
-        if ((rc = dev_upload(pb, &al.li_idx, li.data(), li.size()))) return rc;
-        /* bounds of the general constraints: NPSOL's bl/bu behind the variables and, for the
-         * linear rows, the expanded linear bounds */
-        std::vector<double> bl((size_t)nC + nclin + ncnln), bu(bl.size());
-        if ((rc = ntgb_get_bounds(pb, bl.data(), bu.data()))) return rc;
-        std::vector<double> hl((size_t)std::max(al.m, 1), 0.0), hu((size_t)std::max(al.m, 1), 0.0);
-        for (int i = 0; i < al.n_li; i++) { hl[i] = pb->lin_lb[li[i]]; hu[i] = pb->lin_ub[li[i]]; }
-        for (int i = 0; i < ncnln; i++) { hl[al.n_li + i] = bl[(size_t)nC + nclin + i]; hu[al.n_li + i] = bu[(size_t)nC + nclin + i]; }
-        if ((rc = dev_upload(pb, &al.hl, hl.data(), hl.size()))) return rc;
-        if ((rc = dev_upload(pb, &al.hu, hu.data(), hu.size()))) return rc;
-        std::vector<double> Ad = pb->A;
-        if (Ad.empty()) Ad.push_back(0.0);
-        if ((rc = dev_upload(pb, &al.A, Ad.data(), Ad.size()))) return rc;
-        al.ready = true;
-    }
+    if (al.nr > kSolveMaxNr)
+        return fail(NTGB_ELIMIT, "ntgb_solve_nlp: %d free directions after eliminating the linear equalities (limit %d)",
+                    al.nr, kSolveMaxNr);
     const int nr = al.nr, m = al.m, n_li = al.n_li;
     constexpr int kN1 = 4, kN2 = 12, kNalpha = kN1 + kN2;
     const size_t Pz = (size_t)P, Q = Pz * kNalpha;
@@ -1935,6 +2195,236 @@ int ntgb_solve_nlp(ntgb_problem *pb, int P, double *C, double *f, double *viol_o
     if (viol_out) CUDA_TRY(cudaMemcpyAsync(viol_out, viol, sizeof(double) * Pz, cudaMemcpyDeviceToDevice, st));
     if (iters) CUDA_TRY(cudaMemcpyAsync(iters, its, sizeof(int) * Pz, cudaMemcpyDeviceToDevice, st));
     if (status) CUDA_TRY(cudaMemcpyAsync(status, fin, sizeof(int) * Pz, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int ntgb_solve_sqp(ntgb_problem *pb, int P, double *C, double *f, double *viol_out, int *iters, int *status,
+                   double *lambda, int *istate, const ntgb_sqp_opts *opts, void *stream)
+{
+    if (!pb || !C) return fail(NTGB_EINVAL, "ntgb_solve_sqp: null argument");
+    if (P <= 0) return 0;
+    const ntgb_dims &dm = pb->dims;
+    ntgb_sqp_opts o{100, 1e-6, 1e-8, 1e4, 1e-4, 4};
+    if (opts) {
+        if (opts->max_iter > 0) o.max_iter = opts->max_iter;
+        if (opts->gtol > 0.0) o.gtol = opts->gtol;
+        if (opts->ctol > 0.0) o.ctol = opts->ctol;
+        if (opts->rho_pen > 0.0) o.rho_pen = opts->rho_pen;
+        if (opts->c1 > 0.0) o.c1 = opts->c1;
+        if (opts->check_every > 0) o.check_every = opts->check_every;
+    }
+    DeviceGuard dg(pb->device);
+    if (!dg.ok) return fail(NTGB_ECUDA, "cannot select device %d", pb->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nC = dm.nC, nclin = dm.nclin, ncnln = dm.ncnln;
+    int rc;
+    if ((rc = alm_prepare(pb))) return rc;
+    auto &al = pb->alm;
+    auto &sq = pb->sqp;
+    const int nr = al.nr, m = al.m, n_li = al.n_li;
+    if (nr < 1) return fail(NTGB_EINVAL, "ntgb_solve_sqp: the linear equalities leave no free direction");
+    /* one CTA per problem: 32 threads up to 31 reduced variables, 64 beyond */
+    const int nt = nr < 32 ? 32 : 64;
+    const size_t smem = sqp::sqp_smem_doubles(nr, m, nt) * sizeof(double) + sqp::sqp_smem_ints(nr, m, nt) * sizeof(int);
+    if (smem > (size_t)pb->max_smem_optin)
+        return fail(NTGB_ELIMIT,
+                    "ntgb_solve_sqp: %d reduced variables x %d rows need %zu bytes of shared memory per problem (limit %d): "
+                    "the dense reduced-space QP is meant for short horizons",
+                    nr, m, smem, pb->max_smem_optin);
+    if (!sq.ready) {
+        /* reduced gradients of the linear inequality rows, and W = (Ae Ae')^-1 Ae for the multipliers
+         * of the eliminated equality rows */
+        std::vector<double> ArN((size_t)std::max(n_li, 1) * nr, 0.0);
+        for (int i = 0; i < n_li; i++)
+            for (int k = 0; k < nr; k++) {
+                double a = 0.0;
+                for (int e = 0; e < nC; e++) a += pb->A[al.li[i] + (size_t)e * nclin] * al.hN[(size_t)k * nC + e];
+                ArN[(size_t)i * nr + k] = a;
+            }
+        if ((rc = dev_upload(pb, &sq.ArN, ArN.data(), ArN.size()))) return rc;
+        const int me = (int)al.eq.size();
+        std::vector<double> W((size_t)std::max(me, 1) * nC, 0.0), G((size_t)std::max(me, 1) * std::max(me, 1), 0.0);
+        for (int r = 0; r < me; r++)
+            for (int s = 0; s < me; s++) {
+                double a = 0.0;
+                for (int e = 0; e < nC; e++) a += pb->A[al.eq[r] + (size_t)e * nclin] * pb->A[al.eq[s] + (size_t)e * nclin];
+                G[(size_t)r * me + s] = a;
+            }
+        /* Gauss-Jordan with partial pivoting on [G | Ae]; dependent rows get zero multipliers */
+        for (int r = 0; r < me; r++)
+            for (int e = 0; e < nC; e++) W[(size_t)r * nC + e] = pb->A[al.eq[r] + (size_t)e * nclin];
+        double gmax = 0.0;
+        for (int r = 0; r < me; r++) gmax = std::max(gmax, std::fabs(G[(size_t)r * me + r]));
+        std::vector<char> dead(std::max(me, 1), 0);
+        for (int k = 0; k < me; k++) {
+            int piv = -1;
+            double best = 1e-12 * std::max(gmax, 1e-300);
+            for (int r = k; r < me; r++)
+                if (std::fabs(G[(size_t)r * me + k]) > best) { best = std::fabs(G[(size_t)r * me + k]); piv = r; }
+            if (piv < 0) { dead[k] = 1; continue; }
+            if (piv != k) {
+                for (int s = 0; s < me; s++) std::swap(G[(size_t)k * me + s], G[(size_t)piv * me + s]);
+                for (int e = 0; e < nC; e++) std::swap(W[(size_t)k * nC + e], W[(size_t)piv * nC + e]);
+            }
+            const double d = G[(size_t)k * me + k];
+            for (int s = 0; s < me; s++) G[(size_t)k * me + s] /= d;
+            for (int e = 0; e < nC; e++) W[(size_t)k * nC + e] /= d;
+            for (int r = 0; r < me; r++) {
+                if (r == k) continue;
+                const double t = G[(size_t)r * me + k];
+                if (t == 0.0) continue;
+                for (int s = 0; s < me; s++) G[(size_t)r * me + s] -= t * G[(size_t)k * me + s];
+                for (int e = 0; e < nC; e++) W[(size_t)r * nC + e] -= t * W[(size_t)k * nC + e];
+            }
+        }
+        for (int k = 0; k < me; k++)
+            if (dead[k])
+                for (int e = 0; e < nC; e++) W[(size_t)k * nC + e] = 0.0;
+        if ((rc = dev_upload(pb, &sq.W, W.data(), W.size()))) return rc;
+        std::vector<int> eqi = al.eq;
+        if (eqi.empty()) eqi.push_back(0);
+        if ((rc = dev_upload(pb, &sq.eq_idx, eqi.data(), eqi.size()))) return rc;
+        sq.me = me;
+        sq.ready = true;
+    }
+    constexpr int kN1 = 4, kN2 = 12, kNalpha = kN1 + kN2;
+    const size_t Pz = (size_t)P, Q = Pz * kNalpha;
+    if (Q > 0x7fffffffull) return fail(NTGB_EINVAL, "P*nalpha too large");
+    const size_t mz = (size_t)std::max(m, 1), ncz = (size_t)std::max(ncnln, 1), nlz = (size_t)std::max(nclin, 1);
+    if (Pz > sq.cap) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (sq.blob) cudaFree(sq.blob);
+        if (sq.tblob) cudaFree(sq.tblob);
+        if (sq.iblob) cudaFree(sq.iblob);
+        sq.blob = sq.tblob = nullptr; sq.iblob = nullptr; sq.cap = 0;
+        const size_t nd = Pz * ((size_t)4 * nr + (size_t)nr * nr + 3 * (size_t)nC + 2 * mz + ncz + ncz * dm.sorder + nlz + 8 + 8) + kNalpha;
+        const size_t nt2 = Q * ((size_t)nC + ncz + nlz + 4);
+        CUDA_TRY(cudaMalloc((void **)&sq.blob, nd * sizeof(double)));
+        CUDA_TRY(cudaMalloc((void **)&sq.tblob, nt2 * sizeof(double)));
+        CUDA_TRY(cudaMalloc((void **)&sq.iblob, (Pz * (12 + mz) + 2) * sizeof(int)));
+        sq.cap = Pz;
+    }
+    const size_t cap = sq.cap;
+    double *q = sq.blob;
+    SqpArrays S;
+    S.y = q;      q += cap * nr;
+    S.sprev = q;  q += cap * nr;
+    S.grLold = q; q += cap * nr;
+    S.d = q;      q += cap * nr;
+    S.B = q;      q += cap * nr * nr;
+    double *dC = q;    q += cap * nC;
+    double *g = q;     q += cap * nC;
+    double *gL = q;    q += cap * nC;
+    S.lam = q;    q += cap * mz;
+    double *mu = q;    q += cap * mz;
+    double *cc = q;    q += cap * ncz;
+    double *J = q;     q += cap * ncz * dm.sorder;
+    double *lin = q;   q += cap * nlz;
+    S.scal = q;   q += cap * 8;
+    double *fv = q;    q += cap;
+    double *phi0 = q;  q += cap;
+    double *dphi0 = q; q += cap;
+    double *ab = q;    q += cap;
+    double *pbest = q; q += cap;
+    double *alphas = q;
+    const size_t capq = cap * kNalpha;
+    double *t = sq.tblob;
+    double *Ct = t;    t += capq * nC;
+    double *ct = t;    t += capq * ncz;
+    double *lint = t;  t += capq * nlz;
+    double *ft = t;    t += capq;
+    double *res = t;
+    int *state = sq.iblob, *its = state + cap, *idx = its + cap, *count = idx + cap, *nidx = count + 1;
+    S.flag = nidx + 1;
+    S.istate = S.flag + cap * 8;
+
+    SqpDesc D;
+    D.nC = nC; D.nr = nr; D.m = m; D.n_li = n_li; D.nclin = nclin; D.ncnln = ncnln;
+    D.N = al.N; D.ArN = sq.ArN; D.li_idx = al.li_idx; D.hl = al.hl; D.hu = al.hu;
+    D.gtol = o.gtol; D.ctol = o.ctol; D.rho_pen = o.rho_pen;
+
+    double ha[kNalpha];
+    for (int a = 0; a < kNalpha; a++) ha[a] = std::ldexp(1.0, -a);
+    CUDA_TRY(cudaMemcpyAsync(alphas, ha, sizeof ha, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(res, 0, sizeof(double) * 2 * Q, st));
+    const unsigned grid = (unsigned)((P + 127) / 128);
+    CUDA_TRY(launch(k_sqp_init, grid, 128, st, P, D, S, al.Cpart, C, state, its));
+    CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(int), st));
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_sqp_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    ntgb_eval_args ea;
+    memset(&ea, 0, sizeof ea);
+    ea.P = P; ea.C = C; ea.mode_obj = 2; ea.mode_con = ncnln > 0 ? 2 : -1; ea.f = fv; ea.g = g; ea.c = cc; ea.J = J;
+    ea.jac_layout = ncnln > 0 ? NTGB_JAC_BAND : NTGB_JAC_NONE; ea.stream = st;
+    ntgb_eval_args et;
+    memset(&et, 0, sizeof et);
+    et.P = (int)Q; et.C = Ct; et.mode_obj = 0; et.mode_con = ncnln > 0 ? 0 : -1; et.f = ft; et.c = ct;
+    et.jac_layout = NTGB_JAC_NONE; et.stream = st;
+
+    auto direction = [&]() -> int { /* f, g, c, J, lin at C -> QP -> d, dC, merit and slope; finished problems counted */
+        int r2;
+        if ((r2 = ntgb_eval(pb, &ea))) return r2;
+        if (n_li > 0 && (r2 = ntgb_eval_linear(pb, P, C, lin, nullptr, st))) return r2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)P);
+        cfg.blockDim = dim3((unsigned)nt);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, k_sqp_step, P, pb->tab, D, S, (const double *)fv, (const double *)g, (const double *)cc,
+                                    (const double *)J, (const double *)lin, dC, phi0, dphi0, state, count));
+        return 0;
+    };
+
+    for (int it = 0; it <= o.max_iter; it++) {
+        if ((rc = direction())) return rc;
+        if (it == o.max_iter) break; /* the last pass only evaluates and tests convergence at the final point */
+        if ((it + 1) % o.check_every == 0) {
+            int done = 0;
+            CUDA_TRY(cudaMemcpyAsync(&done, count, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (done >= P) break;
+        }
+        /* Armijo search on the L1 merit, two stages like ntgb_solve_nlp: steps 1 .. 1/8 for every
+         * problem, 2^-4 .. 2^-15 only for the compacted list that found none */
+        const long long totc = (long long)P * kN1 * nC;
+        CUDA_TRY(launch(k_ls_trial, (unsigned)((totc + 255) / 256), 256, st, C, dC, alphas, P, kN1, nC, Ct));
+        et.P = P * kN1;
+        if ((rc = ntgb_eval(pb, &et))) return rc;
+        if (n_li > 0 && (rc = ntgb_eval_linear(pb, et.P, Ct, lint, nullptr, st))) return rc;
+        CUDA_TRY(launch(k_sqp_merit, (unsigned)(((long long)et.P * 32 + 127) / 128), 128, st, et.P, kN1, D, S.scal, ft, ct, lint, res,
+                        (const int *)nullptr));
+        CUDA_TRY(cudaMemsetAsync(nidx, 0, sizeof(int), st));
+        CUDA_TRY(launch(k_alm_pick1, grid, 128, st, res, alphas, P, kN1, o.c1, phi0, dphi0, state, ab, pbest, idx, nidx));
+        int n2 = 0;
+        CUDA_TRY(cudaMemcpyAsync(&n2, nidx, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (n2 > 0) {
+            const long long tot2 = (long long)n2 * kN2 * nC;
+            CUDA_TRY(launch(k_ls_trial_idx, (unsigned)((tot2 + 255) / 256), 256, st, C, dC, alphas + kN1, idx, n2, kN2, nC, Ct));
+            et.P = n2 * kN2;
+            if ((rc = ntgb_eval(pb, &et))) return rc;
+            if (n_li > 0 && (rc = ntgb_eval_linear(pb, et.P, Ct, lint, nullptr, st))) return rc;
+            CUDA_TRY(launch(k_sqp_merit, (unsigned)(((long long)et.P * 32 + 127) / 128), 128, st, et.P, kN2, D, S.scal, ft, ct, lint,
+                            res, (const int *)idx));
+            CUDA_TRY(launch(k_alm_pick2, (unsigned)((n2 + 127) / 128), 128, st, res, alphas + kN1, idx, n2, kN2, o.c1, phi0, dphi0,
+                            ab, pbest));
+        }
+        CUDA_TRY(launch(k_sqp_update, grid, 128, st, P, D, S, al.Cpart, phi0, ab, pbest, C, state, its, count));
+    }
+    if (lambda || istate) {
+        /* gL = g - A_in' l_in - J' l_nl in the full space (k_alm_grad adds dh' mu: mu = -lambda) */
+        const long long totm = (long long)P * mz;
+        CUDA_TRY(launch(k_scale_copy, (unsigned)((totm + 255) / 256), 256, st, totm, -1.0, (const double *)S.lam, mu));
+        const long long tot = (long long)P * nC;
+        CUDA_TRY(launch(k_alm_grad, (unsigned)((tot + 127) / 128), 128, st, P, pb->tab, nclin, n_li, al.li_idx, al.A, g, J, mu, gL));
+        CUDA_TRY(launch(k_sqp_outputs, grid, 128, st, P, D, S, sq.me, sq.eq_idx, sq.W, gL, lambda, istate));
+    }
+    if (f) CUDA_TRY(cudaMemcpyAsync(f, fv, sizeof(double) * Pz, cudaMemcpyDeviceToDevice, st));
+    if (viol_out) CUDA_TRY(cudaMemcpy2DAsync(viol_out, sizeof(double), S.scal + 3, 8 * sizeof(double), sizeof(double), Pz,
+                                             cudaMemcpyDeviceToDevice, st));
+    if (iters) CUDA_TRY(cudaMemcpyAsync(iters, its, sizeof(int) * Pz, cudaMemcpyDeviceToDevice, st));
+    if (status) CUDA_TRY(cudaMemcpyAsync(status, state, sizeof(int) * Pz, cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return 0;
 }

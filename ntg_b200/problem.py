@@ -13,7 +13,7 @@ from typing import Dict, Optional
 import numpy as np
 
 from . import abi
-from .abi import (JAC_BAND, JAC_DENSE, JAC_NONE, BuiltSetup, NtgbDims, NtgbEvalArgs, NtgbPack, SolveOpts, NlpOpts,
+from .abi import (JAC_BAND, JAC_DENSE, JAC_NONE, BuiltSetup, NtgbDims, NtgbEvalArgs, NtgbPack, SolveOpts, NlpOpts, SqpOpts,
                   ProblemSpec, c_double_p, c_int_p)
 
 _LIBDIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
@@ -54,6 +54,8 @@ def core() -> C.CDLL:
         lib.ntgb_solve_nlp.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]
         lib.ntgb_solve_nlp.restype = C.c_int
+        lib.ntgb_solve_sqp.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 9
+        lib.ntgb_solve_sqp.restype = C.c_int
         lib.ntgb_peer_table_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]
         lib.ntgb_peer_table_open.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
         lib.ntgb_peer_table_close.argtypes = [C.c_void_p, C.c_void_p]
@@ -324,6 +326,26 @@ class Problem:
         _check(core().ntgb_solve_nlp(self._h, P, Cdev.data_ptr(), f.data_ptr(), v.data_ptr(), it.data_ptr(),
                                      stt.data_ptr(), C.addressof(opts), st))
         return f, v, it, stt
+
+    def solve_sqp(self, Cdev, max_iter=0, gtol=0.0, ctol=0.0, rho_pen=0.0, c1=0.0, check_every=0, multipliers=False):
+        """batched SQP solve (ntgb_solve_sqp); Cdev [P][nC] is overwritten.  Returns f [P], violation [P],
+        iters [P], status [P] and, with multipliers=True, lambda and istate [P][nclin + ncnln] (NPSOL's order)."""
+        import torch
+        P, d = Cdev.shape[0], self.dims
+        f = torch.zeros(P, dtype=torch.float64, device=Cdev.device)
+        v = torch.zeros(P, dtype=torch.float64, device=Cdev.device)
+        it = torch.zeros(P, dtype=torch.int32, device=Cdev.device)
+        stt = torch.zeros(P, dtype=torch.int32, device=Cdev.device)
+        lam = ist = None
+        if multipliers:
+            lam = torch.zeros((P, d.nclin + d.ncnln), dtype=torch.float64, device=Cdev.device)
+            ist = torch.zeros((P, d.nclin + d.ncnln), dtype=torch.int32, device=Cdev.device)
+        opts = SqpOpts(int(max_iter), float(gtol), float(ctol), float(rho_pen), float(c1), int(check_every))
+        st = torch.cuda.current_stream(Cdev.device).cuda_stream
+        _check(core().ntgb_solve_sqp(self._h, P, Cdev.data_ptr(), f.data_ptr(), v.data_ptr(), it.data_ptr(), stt.data_ptr(),
+                                     lam.data_ptr() if multipliers else None, ist.data_ptr() if multipliers else None,
+                                     C.addressof(opts), st))
+        return (f, v, it, stt, lam, ist) if multipliers else (f, v, it, stt)
 
     def spline_interp(self, Cdev, tdev):
         import torch

@@ -523,9 +523,9 @@ def time_e2e(torch, pb, spec, cfg, P, steps, warmup, full: bool):
 
 
 def time_solvers(torch, device, fast):
-    """Wall time of the two batched solvers on the lane-change problem of examples/kincar.c:
-    ntgb_solve_eq (linear equalities only, as shipped) and ntgb_solve_nlp (active speed and
-    curvature bounds).  Host wall clock around the synchronous C call, after one warm-up solve."""
+    """Wall time of the batched solvers on the lane-change problem of examples/kincar.c:
+    ntgb_solve_eq (linear equalities only, as shipped), ntgb_solve_nlp and ntgb_solve_sqp (active speed
+    and curvature bounds).  Host wall clock around the synchronous C call, after one warm-up solve."""
     import dataclasses
     from ntg_b200 import Problem
     out = {}
@@ -565,6 +565,17 @@ def time_solvers(torch, device, fast):
                         "problems": P2, "ms": dt * 1e3, "problems_per_s": P2 / dt,
                         "iterations_mean": float(it.float().mean()), "converged_frac": float((st >= 1).float().mean()),
                         "violation_max": float(v.max())}
+    pb.solve_sqp(X2.clone())
+    C3 = X2.clone()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    _, v, it, st = pb.solve_sqp(C3)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out["solve_sqp"] = {"workload": "the same 16384 problems and starts; SQP (dual active-set QP per problem in shared memory, BFGS)",
+                        "problems": P2, "ms": dt * 1e3, "problems_per_s": P2 / dt,
+                        "iterations_mean": float(it.float().mean()), "converged_frac": float((st == 1).float().mean()),
+                        "violation_max": float(v[st == 1].max()) if bool((st == 1).any()) else None}
     pb.close()
     torch.cuda.empty_cache()
     return out

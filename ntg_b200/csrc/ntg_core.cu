@@ -882,7 +882,7 @@ struct SqpDesc {
 
 /* per-problem solver state, problem-major */
 struct SqpArrays {
-    double *y, *B, *lam, *sprev, *grLold, *d, *scal;
+    double *y, *B, *lam, *sprev, *grLold, *grold, *d, *scal;
     int *flag, *istate;
 };
 
@@ -980,7 +980,7 @@ __global__ void k_sqp_step(int P, ntgb_devtab T, SqpDesc D, SqpArrays S, const d
     __syncthreads();
     const sqp::Coop cg{tid, nt, tid & 31, nt < 32 ? nt : 32};
     const sqp::StepState st{S.y + (size_t)p * nr, S.B + (size_t)p * nr * nr, S.lam + (size_t)p * m, S.sprev + (size_t)p * nr,
-                            S.grLold + (size_t)p * nr, S.d + (size_t)p * nr, S.scal + (size_t)p * 8, S.flag + (size_t)p * 8,
+                            S.grLold + (size_t)p * nr, S.grold + (size_t)p * nr, S.d + (size_t)p * nr, S.scal + (size_t)p * 8, S.flag + (size_t)p * 8,
                             S.istate + (size_t)p * m};
     const sqp::StepOpts so{D.gtol, D.ctol, D.rho_pen};
     sqp::sqp_step(cg, w, st, so, f[p], gr, hrow, D.hl, D.hu, Bm, Lm, vec);
@@ -2298,7 +2298,7 @@ int ntgb_solve_sqp(ntgb_problem *pb, int P, double *C, double *f, double *viol_o
         if (sq.tblob) cudaFree(sq.tblob);
         if (sq.iblob) cudaFree(sq.iblob);
         sq.blob = sq.tblob = nullptr; sq.iblob = nullptr; sq.cap = 0;
-        const size_t nd = Pz * ((size_t)4 * nr + (size_t)nr * nr + 3 * (size_t)nC + 2 * mz + ncz + ncz * dm.sorder + nlz + 8 + 8) + kNalpha;
+        const size_t nd = Pz * ((size_t)5 * nr + (size_t)nr * nr + 3 * (size_t)nC + 2 * mz + ncz + ncz * dm.sorder + nlz + 8 + 8) + kNalpha;
         const size_t nt2 = Q * ((size_t)nC + ncz + nlz + 4);
         CUDA_TRY(cudaMalloc((void **)&sq.blob, nd * sizeof(double)));
         CUDA_TRY(cudaMalloc((void **)&sq.tblob, nt2 * sizeof(double)));
@@ -2311,6 +2311,7 @@ int ntgb_solve_sqp(ntgb_problem *pb, int P, double *C, double *f, double *viol_o
     S.y = q;      q += cap * nr;
     S.sprev = q;  q += cap * nr;
     S.grLold = q; q += cap * nr;
+    S.grold = q;  q += cap * nr;
     S.d = q;      q += cap * nr;
     S.B = q;      q += cap * nr * nr;
     double *dC = q;    q += cap * nC;

@@ -311,8 +311,9 @@ void ntg(int nout, double *bps, int nbps, int *kninterv, double **knots, int *or
     if (!npsol) {
         /* No NPSOL in the process: the library's own batched solvers stand in (P = 1).  Problems
          * of the shipped examples' class (no nonlinear constraints, linear equalities only) go to the
-         * reduced-space BFGS (ntgb_solve_eq), everything else to the augmented-Lagrangian driver
-         * (ntgb_solve_nlp).  NTG_B200_NO_BUILTIN_SOLVER=1 switches this off. */
+         * reduced-space BFGS (ntgb_solve_eq), everything else to the SQP solver (ntgb_solve_sqp) with
+         * the augmented-Lagrangian driver (ntgb_solve_nlp) behind it.  NTG_B200_NO_BUILTIN_SOLVER=1
+         * switches this off. */
         const bool builtin = getenv("NTG_B200_NO_BUILTIN_SOLVER") == nullptr;
         bool eq_only = NPncnln == 0;
         for (int i = 0; eq_only && i < NPnclin; i++) eq_only = bl[NPn + i] == bu[NPn + i];
@@ -323,29 +324,69 @@ void ntg(int nout, double *bps, int nbps, int *kninterv, double **knots, int *or
             int st = 0;
             double fv = 0.0;
             cudaSetDevice(device);
+            const int ngen = NPnclin + NPncnln;
+            double *dlam = nullptr;
+            int *dist = nullptr;
+            const char *used = "reduced-space BFGS";
+            bool have_mult = false;
             if (cudaMalloc((void **)&dC, sizeof(double) * ((size_t)NPn + 2)) == cudaSuccess &&
                 cudaMalloc((void **)&dst, sizeof(int) * 2) == cudaSuccess &&
+                cudaMalloc((void **)&dlam, sizeof(double) * (size_t)(ngen > 0 ? ngen : 1)) == cudaSuccess &&
+                cudaMalloc((void **)&dist, sizeof(int) * (size_t)(ngen > 0 ? ngen : 1)) == cudaSuccess &&
                 cudaMemcpy(dC, initialguess, sizeof(double) * NPn, cudaMemcpyHostToDevice) == cudaSuccess) {
-                /* equalities only: reduced-space BFGS; anything else: augmented Lagrangian on top of it */
-                rc = eq_only ? ntgb_solve_eq(pb, 1, dC, dC + NPn, dst, dst + 1, nullptr, nullptr)
-                             : ntgb_solve_nlp(pb, 1, dC, dC + NPn, dC + NPn + 1, dst, dst + 1, nullptr, nullptr);
+                /* equalities only: reduced-space BFGS.  Anything else: the SQP solver (NPSOL's method:
+                 * active-set QP subproblems, quasi-Newton Hessian; returns multipliers and the active set);
+                 * if the dense reduced QP does not fit in shared memory or it does not converge, the
+                 * augmented-Lagrangian driver from the same guess. */
+                if (eq_only) {
+                    rc = ntgb_solve_eq(pb, 1, dC, dC + NPn, dst, dst + 1, nullptr, nullptr);
+                } else {
+                    used = "SQP solver (dual active-set QP, BFGS)";
+                    rc = ntgb_solve_sqp(pb, 1, dC, dC + NPn, dC + NPn + 1, dst, dst + 1, dlam, dist, nullptr, nullptr);
+                    int s1 = 0;
+                    if (rc == 0 && cudaMemcpy(&s1, dst + 1, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) rc = NTGB_ECUDA;
+                    have_mult = rc == 0 && s1 == 1;
+                    if (rc == NTGB_ELIMIT || (rc == 0 && s1 != 1)) {
+                        used = "augmented-Lagrangian / reduced-space BFGS";
+                        rc = cudaMemcpy(dC, initialguess, sizeof(double) * NPn, cudaMemcpyHostToDevice) == cudaSuccess
+                                 ? ntgb_solve_nlp(pb, 1, dC, dC + NPn, dC + NPn + 1, dst, dst + 1, nullptr, nullptr)
+                                 : NTGB_ECUDA;
+                    }
+                }
                 if (rc == 0 && cudaMemcpy(&st, dst + 1, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess &&
                     cudaMemcpy(&fv, dC + NPn, sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess &&
                     cudaMemcpy(initialguess, dC, sizeof(double) * NPn, cudaMemcpyDeviceToHost) == cudaSuccess) {
                     if (objective) *objective = fv;
                     /* NPSOL's codes: 0 optimal, 1 no further improvement possible, 4 iteration limit
-                     * (solve_nlp: 6 = not converged, the nonlinear constraints may be violated) */
+                     * (6 = not converged, the nonlinear constraints may be violated) */
                     if (inform) *inform = st == 1 ? 0 : (st == 2 ? 1 : (eq_only ? 4 : 6));
+                    if (have_mult) {
+                        /* NPSOL's layout (src/ntg.h:64-68): n variables (no bounds in NTG: free, multiplier 0),
+                         * then the nclin linear and the ncnln nonlinear rows */
+                        if (istate) {
+                            for (int i = 0; i < NPn; i++) istate[i] = 0;
+                            if (ngen > 0 && cudaMemcpy(istate + NPn, dist, sizeof(int) * ngen, cudaMemcpyDeviceToHost) != cudaSuccess)
+                                have_mult = false;
+                        }
+                        if (clambda) {
+                            for (int i = 0; i < NPn; i++) clambda[i] = 0.0;
+                            if (ngen > 0 && cudaMemcpy(clambda + NPn, dlam, sizeof(double) * ngen, cudaMemcpyDeviceToHost) != cudaSuccess)
+                                have_mult = false;
+                        }
+                    }
                     fprintf(stderr,
                             "ntg: NPSOL (npsol_) is not linked into this process; solved with ntg_b200's built-in\n"
                             "     %s instead (n=%d, nclin=%d, ncnln=%d).\n"
-                            "     istate, clambda and R are not set on this path.\n",
-                            eq_only ? "reduced-space BFGS" : "augmented-Lagrangian / reduced-space BFGS", NPn, NPnclin,
-                            NPncnln);
+                            "     %s\n",
+                            used, NPn, NPnclin, NPncnln,
+                            have_mult ? "istate and clambda are set (NPSOL's layout); R is not."
+                                      : "istate, clambda and R are not set on this path.");
                 } else if (rc == 0) {
                     rc = NTGB_ECUDA;
                 }
             }
+            if (dlam) cudaFree(dlam);
+            if (dist) cudaFree(dist);
             if (dC) cudaFree(dC);
             if (dst) cudaFree(dst);
             if (rc != 0) fprintf(stderr, "ntg: built-in solver failed: %s\n", ntgb_last_error());

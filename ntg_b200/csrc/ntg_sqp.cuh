@@ -386,6 +386,7 @@ struct StepState {
     double *lam;    /* [m] multipliers of the last QP */
     double *sprev;  /* [nr] the last accepted step alpha*d */
     double *grLold; /* [nr] gr - Ar'lam at the previous point, with the multipliers of ITS QP */
+    double *grold;  /* [nr] gr at the previous point */
     double *d;      /* [nr] out: search direction */
     double *scal;   /* [0] nu  [1] phi0 (out)  [2] dphi0 (out)  [3] violation, scaled max (out)  [4] kkt (out) */
     int *flag;      /* [0] a previous step exists  [1] that step was a Gauss-Newton (restoration) step
@@ -419,6 +420,35 @@ NTG_HD void sqp_step(const C &cg, const Qp &w, const StepState &S, const StepOpt
     const bool reset = S.flag[2] != 0;
     bool fresh = reset || S.flag[3] != 0;
     /* ---- damped BFGS update with the step that led here ---- */
+    if (!reset && S.flag[0] && S.flag[1]) {
+        /* it was a Gauss-Newton step, whose multipliers say nothing about the Lagrangian: B only takes
+         * the SCALE of the cost's curvature along the step (never down), so that an identity that is
+         * orders of magnitude too small does not send the next steps far outside the model */
+        for (int k = cg.tid; k < n; k += cg.nt) {
+            double b = 0.0;
+            for (int j = 0; j < n; j++) b += Bm[k * ld + j] * S.sprev[j];
+            Bs[k] = b;
+        }
+        cg.sync();
+        if (cg.tid == 0) {
+            double sBs = 0.0, suf = 0.0;
+            for (int k = 0; k < n; k++) {
+                sBs += S.sprev[k] * Bs[k];
+                suf += S.sprev[k] * (gr[k] - S.grold[k]);
+            }
+            w.sh[0] = (sBs > 0.0 && suf > sBs) ? fmin(suf / sBs, 1e8) : 1.0;
+        }
+        cg.sync();
+        const double fac = w.sh[0];
+        if (fac != 1.0) {
+            for (int e = cg.tid; e < n * n; e += cg.nt) {
+                const int i = e / n, j = e - i * n;
+                Bm[i * ld + j] *= fac;
+            }
+            fresh = false;
+        }
+        cg.sync();
+    }
     if (!reset && S.flag[0] && !S.flag[1]) {
         for (int k = cg.tid; k < n; k += cg.nt) {
             double a = gr[k];
@@ -583,6 +613,7 @@ NTG_HD void sqp_step(const C &cg, const Qp &w, const StepState &S, const StepOpt
     for (int k = cg.tid; k < n; k += cg.nt) {
         S.d[k] = w.x[k];
         S.grLold[k] = grL[k];
+        S.grold[k] = gr[k];
     }
     for (int i = cg.tid; i < m; i += cg.nt) {
         S.lam[i] = w.lam[i];

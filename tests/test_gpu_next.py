@@ -156,15 +156,19 @@ core = problem.core()
 n = spec.nC
 inform, obj = C.c_int(0), C.c_double(0.0)
 x0 = (C.c_double * n)(*([1.0] * n))
+ntot = n + spec.nclin + spec.ncnln
+istate, clambda = (C.c_int * ntot)(*([-99] * ntot)), (C.c_double * ntot)()
 core.ntg.restype = None
 core.ntg(s.nout, s.bps, s.nbps, s.kninterv, s.knots, s.order, s.mult, s.maxderiv, x0,
          s.nlic, s.lic, s.nltc, s.ltc, s.nlfc, s.lfc, 0, None, s.nnltc, C.c_void_p(s.nltcf), 0, None,
          0, None, s.ntrajectoryconstrav, s.trajectoryconstrav, 0, None,
          s.lowerb, s.upperb, 0, None, 1, C.c_void_p(s.ucf), 0, None, 0, None,
          s.ntrajectorycostav, s.trajectorycostav, 0, None,
-         (C.c_int * (n + 8 + 3 * 20))(), (C.c_double * (n + 8 + 3 * 20))(), (C.c_double * ((n + 1) ** 2))(),
+         istate, clambda, (C.c_double * ((n + 1) ** 2))(),
          C.byref(inform), C.byref(obj))
 print("INFORM", inform.value)
+print("ISTATE", " ".join(str(v) for v in istate))
+print("CLAMBDA", " ".join("%%.17g" %% v for v in clambda))
 print("OBJ %%.17g" %% obj.value)
 print("X", " ".join("%%.17g" %% v for v in x0))
 """
@@ -192,12 +196,13 @@ def test_ntg_without_npsol_reports_it():
 
 def test_ntg_without_npsol_solves_constrained_problems(port):
     """NPSOL absent, van der Pol with the nonlinear input constraint |u| <= 2 (pack VDP-C): ntg()
-    falls back to the augmented-Lagrangian solver and returns a feasible point that is at least as
-    good as the start."""
+    falls back to the built-in SQP solver and returns a KKT point -- feasible, and stationary by the
+    ORACLE's gradient and Jacobian with the multipliers ntg() hands back in NPSOL's clambda / istate
+    layout (/root/reference/src/ntg.h:64-68)."""
     out, err = _run_ntg_no_npsol(True)
     lines = dict(l.split(" ", 1) for l in out.strip().splitlines() if " " in l)
-    assert int(lines["INFORM"]) in (0, 1), out + err
-    assert "augmented-Lagrangian" in err
+    assert int(lines["INFORM"]) == 0, out + err
+    assert "SQP solver" in err and "istate and clambda are set" in err
     x = np.array([float(v) for v in lines["X"].split()])
     spec = configs.vanderpol(20, constraints=True)
     o = port.eval(spec, x[None, :], mode_obj=2, mode_con=2, dense=False, band=False, linear=True)
@@ -207,6 +212,19 @@ def test_ntg_without_npsol_solves_constrained_problems(port):
     lb, ub = o["bl"][nC + spec.nclin:], o["bu"][nC + spec.nclin:]
     assert (o["c"][0] >= lb - 2e-6).all() and (o["c"][0] <= ub + 2e-6).all()
     assert abs(float(lines["OBJ"]) - o["f"][0]) <= 1e-12 * abs(o["f"][0])
+    ist = np.array([int(v) for v in lines["ISTATE"].split()])
+    lam = np.array([float(v) for v in lines["CLAMBDA"].split()])
+    assert ist.size == nC + spec.nclin + spec.ncnln and (ist[:nC] == 0).all() and (lam[:nC] == 0).all()
+    assert (ist[nC:nC + spec.nclin] == 3).all(), "the linear rows of van der Pol are equalities"
+    d = port.eval(spec, x[None, :], mode_obj=2, mode_con=2, dense=True, band=False)
+    Jd = np.nan_to_num(d["Jdense"][0], nan=0.0)
+    Jd = Jd.T if Jd.shape[0] == nC and Jd.shape[1] != nC else Jd
+    r = o["g"][0] - A.T @ lam[nC:nC + spec.nclin] - Jd.T @ lam[nC + spec.nclin:]
+    assert np.abs(r).max() <= 1e-5 * max(1.0, np.abs(o["g"][0]).max()), np.abs(r).max()
+    sn, ln = ist[nC + spec.nclin:], lam[nC + spec.nclin:]
+    assert set(np.unique(sn)) <= {0, 1, 2}
+    assert (np.abs(o["c"][0] - lb)[sn == 1] <= 1e-6).all() and (np.abs(o["c"][0] - ub)[sn == 2] <= 1e-6).all()
+    assert (ln[sn == 1] >= 0).all() and (ln[sn == 2] <= 0).all() and (ln[sn == 0] == 0).all()
 
 
 def test_ntg_without_npsol_solves_equality_problems(port):

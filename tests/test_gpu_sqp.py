@@ -161,6 +161,18 @@ def test_sqp_edge_cases(port):
     assert (np.abs(o["c"][ok]).max(axis=1) <= 1.0 + 1e-6).all()
     assert (f.cpu().numpy()[ok] <= 1e-8).all()   # positive definite quadratic, C = 0 feasible
     pb.close()
+    # 39 free directions: the CTA is two warps (64 threads) instead of one
+    spec = configs.high_order(order=6, mult=3, ninterv=12, nbps=49, name="sqp_hi39")
+    assert spec.nC == 39 and spec.nclin == 0
+    pb = Problem(spec, 0)
+    X = np.random.default_rng(8).uniform(-0.5, 0.5, (8, spec.nC))
+    Cd = torch.from_numpy(X).cuda()
+    f, v, it, st = pb.solve_sqp(Cd, max_iter=400)
+    ok = st.cpu().numpy() == 1
+    assert ok.mean() >= 0.85, (st.cpu().numpy(), it.cpu().numpy())
+    o = port.eval(spec, Cd.cpu().numpy(), mode_obj=2, mode_con=0, dense=False, band=False)
+    assert (np.abs(o["c"][ok]).max(axis=1) <= 1.0 + 1e-6).all() and (f.cpu().numpy()[ok] <= 1e-8).all()
+    pb.close()
     spec, _ = configs.get("cfg5")
     pb = Problem(spec, 0)
     with pytest.raises(NtgError):

@@ -37,7 +37,7 @@ int sqp_host_qp(int n, int m, const double *G, const double *g0, const double *A
 
 /* one SQP iteration: state arrays as in StepState (y unused here) */
 void sqp_host_step(int n, int m, double f, const double *gr_in, const double *h, const double *hl, const double *hu,
-                   const double *A, double *B, double *lam, double *sprev, double *grLold, double *d, double *scal,
+                   const double *A, double *B, double *lam, double *sprev, double *grLold, double *grold, double *d, double *scal,
                    int *flag, int *istate, double gtol, double ctol, double rho_pen)
 {
     const int nt = 1;
@@ -50,7 +50,7 @@ void sqp_host_step(int n, int m, double f, const double *gr_in, const double *h,
     for (int i = 0; i < m; i++)
         for (int k = 0; k < n; k++) w.A[i * w.ld + k] = A[i * n + k];
     memcpy(gr, gr_in, sizeof(double) * n);
-    StepState S{nullptr, B, lam, sprev, grLold, d, scal, flag, istate};
+    StepState S{nullptr, B, lam, sprev, grLold, grold, d, scal, flag, istate};
     StepOpts o{gtol, ctol, rho_pen};
     sqp_step(cg, w, S, o, f, gr, h, hl, hu, Bm, Lm, vec);
 }

@@ -233,7 +233,7 @@ def row_viol(h, hl, hu):
     return np.maximum(np.maximum(np.where(hl > -BIG, hl - h, 0.0), np.where(hu < BIG, h - hu, 0.0)), 0.0)
 
 
-def sqp(nlp, y0, gtol=1e-6, ctol=1e-8, max_iter=60, verbose=False, rho_pen=1e4, init_scale=False, restor_hard=False, scalar_nu=True):
+def sqp(nlp, y0, gtol=1e-6, ctol=1e-8, max_iter=60, verbose=False, rho_pen=1e4, init_scale=False, restor_hard=False, scalar_nu=True, restor_scale=True):
     """One problem.  Returns dict(y, f, viol, iters, evals, status, lam, istate).
 
     Per iteration: QP on the reduced space (Goldfarb-Idnani).  If the linearised constraints are
@@ -327,6 +327,7 @@ def sqp(nlp, y0, gtol=1e-6, ctol=1e-8, max_iter=60, verbose=False, rho_pen=1e4, 
         s = alpha * d
         y = y + s
         grL_old = gr - Jr.T @ lam_new
+        gr_old = gr
         f, gr, h, Jr = nlp.eval(y)
         uu = (gr - Jr.T @ lam_new) - grL_old
         Bs = B @ s
@@ -334,7 +335,7 @@ def sqp(nlp, y0, gtol=1e-6, ctol=1e-8, max_iter=60, verbose=False, rho_pen=1e4, 
         su = s @ uu
         if not restor:
             if not scaled and su > 0:
-                B = np.eye(nr) * (uu @ uu) / su
+                B = B * (su / sBs if init_scale == 2 else (uu @ uu) / su * nr / np.trace(B))
                 Bs = B @ s
                 sBs = s @ Bs
                 scaled = True
@@ -344,6 +345,10 @@ def sqp(nlp, y0, gtol=1e-6, ctol=1e-8, max_iter=60, verbose=False, rho_pen=1e4, 
                 su = s @ uu
             if sBs > 0 and su > 0:
                 B = B - np.outer(Bs, Bs) / sBs + np.outer(uu, uu) / su
+        elif restor_scale:
+            suf = s @ (gr - gr_old)
+            if sBs > 0 and suf > sBs:
+                B = B * min(suf / sBs, 1e8)
         lam = lam_new
     viol = row_viol(h, hl, hu)
     return dict(y=y, C=nlp.Cpart + nlp.N @ y, f=f, viol=viol.max() if m else 0.0, iters=it + 1, evals=nlp.nevals - ev0,
@@ -360,18 +365,18 @@ def sqp_via_core(lib, nlp, y0, gtol=1e-6, ctol=1e-8, max_iter=60, rho_pen=1e4, n
     hl, hu = np.ascontiguousarray(nlp.hl), np.ascontiguousarray(nlp.hu)
     y = y0.copy()
     B = np.eye(nr).ravel().copy()
-    lam, sprev, grLold, d = np.zeros(max(m, 1)), np.zeros(nr), np.zeros(nr), np.zeros(nr)
+    lam, sprev, grLold, grold, d = np.zeros(max(m, 1)), np.zeros(nr), np.zeros(nr), np.zeros(nr), np.zeros(nr)
     scal = np.zeros(8)
     flag = np.zeros(8, dtype=np.int32)
     flag[3] = 1
     istate = np.zeros(max(m, 1), dtype=np.int32)
     ev0 = nlp.nevals
     status = 0
-    lib.sqp_host_step.argtypes = [C.c_int, C.c_int, C.c_double] + [C.POINTER(C.c_double)] * 11 + [C.POINTER(C.c_int)] * 2 + [C.c_double] * 3
+    lib.sqp_host_step.argtypes = [C.c_int, C.c_int, C.c_double] + [C.POINTER(C.c_double)] * 12 + [C.POINTER(C.c_int)] * 2 + [C.c_double] * 3
     for it in range(max_iter):
         f, gr, h, Jr = nlp.eval(y)
         gr, h, Jr = np.ascontiguousarray(gr), np.ascontiguousarray(h), np.ascontiguousarray(Jr)
-        lib.sqp_host_step(nr, m, f, dp(gr), dp(h), dp(hl), dp(hu), dp(Jr), dp(B), dp(lam), dp(sprev), dp(grLold), dp(d), dp(scal),
+        lib.sqp_host_step(nr, m, f, dp(gr), dp(h), dp(hl), dp(hu), dp(Jr), dp(B), dp(lam), dp(sprev), dp(grLold), dp(grold), dp(d), dp(scal),
                           ip(flag), ip(istate), gtol, ctol, rho_pen)
         if flag[5] != 0:
             status = int(flag[5])

@@ -826,19 +826,23 @@ def main():
             del ring2
             pb2.close()
             torch.cuda.empty_cache()
-        # the same workload three more ways: bit-identical variant, NPSOL's dense column-major
-        # Jacobian layout (src/ntg.c:217-220), and the general kernel K1 on a shape neither
-        # register-table kernel takes (outputs with different spline setups, > 256 breakpoints)
-        extra = [("cfg4_exact", a.workload, None, False, JAC_BAND, 20),
-                 ("cfg4_dense_npsol_layout", a.workload, None, fast, JAC_DENSE, 20),
-                 ("k1_general_endpoint_320bps", "endpt", configs.endpoint(320, name="endpoint_320bps_x16384"), fast, JAC_BAND, 10)]
-        for key, cfg, s3, fst, jac, st in extra:
+        # the same workload two more ways: bit-identical variant, NPSOL's dense column-major
+        # Jacobian layout (src/ntg.c:217-220); then outputs with DIFFERENT spline setups (no cluster
+        # kernel) on longer horizons: 320 breakpoints (K1s on CTAs of 512 threads) and 640 (the
+        # general kernel K1, the fallback for everything the register-table kernels do not take)
+        extra = [("cfg4_exact", a.workload, None, False, JAC_BAND, 20, None),
+                 ("cfg4_dense_npsol_layout", a.workload, None, fast, JAC_DENSE, 20, None),
+                 ("nonuniform_endpoint_320bps", "endpt", configs.endpoint(320, name="endpoint_320bps_x16384"), fast, JAC_BAND, 10,
+                  "ntgb::ntg_eval_small_kernel<endpt, BLOCK=512> (K1s, one CTA of 512 threads per SM)"),
+                 ("k1_general_endpoint_640bps", "endpt", configs.endpoint(640, name="endpoint_640bps_x8192"), fast, JAC_BAND, 10,
+                  "ntgb::ntg_eval_kernel<endpt> (K1 general)")]
+        for key, cfg, s3, fst, jac, st, kname in extra:
             try:
                 if s3 is None:
                     s3, P3 = configs.get(cfg)
                     X3 = configs.coefficients(cfg, P3, s3)
                 else:
-                    P3 = 16384
+                    P3 = 16384 if s3.nbps <= 512 else 8192
                     X3 = configs.coefficients("other", P3, s3)
                 pb3 = Problem(s3, local, fast=fst)
                 ring3 = make_ring(torch, pb3, s3, X3, jac)
@@ -852,6 +856,8 @@ def main():
                                "bytes_per_eval": bpe, "evals_per_s": P3 / (r3["ms_per_step"] * 1e-3),
                                "ms_per_step": r3["ms_per_step"], "kernel_ms": r3["kernel_ms"],
                                "algorithmic_gbs": gbs, "roofline_frac": gbs / peak}
+                if kname:
+                    others[key]["kernel"] = kname
                 del ring3, X3
                 pb3.close()
                 torch.cuda.empty_cache()

@@ -320,8 +320,8 @@ __device__ __noinline__ void push_pairs(const double *res_s, double2 *const *dst
 
 /* HOT = the solver's steady state, known at compile time: funobj mode 2 + funcon mode 2, Jacobian
  * in band layout, f / g / c / J all requested, Z not requested. */
-template <class PK, bool FULL, bool HOT = false, bool PEERS = true>
-__global__ void __launch_bounds__(256, 2)
+template <class PK, bool FULL, bool HOT = false, bool PEERS = true, int BLOCK = 256>
+__global__ void __launch_bounds__(BLOCK, 512 / BLOCK)
 ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R, int segtot, int pdl)
 {
     constexpr int NOUT = PK::kNout;
@@ -842,7 +842,8 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
 template <class PK>
 __host__ inline bool small_shape_ok(const ntgb_devtab &T)
 {
-    return pk_tab_doubles<PK>() <= 64 && T.nbps <= 256 && T.band_tile == T.nbps; /* band rows of nbps values */
+    /* up to 256 breakpoints: CTAs of 256 threads, two per SM; up to 512: one CTA of 512 threads per SM */
+    return pk_tab_doubles<PK>() <= 64 && T.nbps <= 512 && T.band_tile == T.nbps; /* band rows of nbps values */
 }
 
 template <class PK>
@@ -850,7 +851,8 @@ int launch_eval_small(const ntgb_launch *L)
 {
     const ntgb_devtab &T = L->tab;
     const int nbps = T.nbps, P = L->args.P;
-    int block = 256;
+    const bool wide = nbps > 256; /* one problem per round on a CTA of 512 threads (same registers per thread, one CTA per SM) */
+    int block = wide ? 512 : 256;
     int G = block / nbps;
     if (G > P) {
         G = P > 0 ? P : 1;
@@ -867,14 +869,14 @@ int launch_eval_small(const ntgb_launch *L)
     /* R rounds per tile: enough (problem, column) chains to fill the CTA in phase B; for small
      * batches, enough problems per tile that the whole batch is ONE wave of resident CTAs (a
      * second, mostly empty wave would double the latency); within ~100 KB of shared memory. */
-    const int slots = 2 * L->sm_count; /* __launch_bounds__(256, 2) */
+    const int slots = (wide ? 1 : 2) * L->sm_count; /* __launch_bounds__(256, 2) / (512, 1) */
     int R = (block + G * (T.nC + 1) - 1) / (G * (T.nC + 1));
     const int r_wave = (int)(((long long)P + (long long)G * slots - 1) / ((long long)G * slots));
     if (r_wave <= 8) R = r_wave;   /* single wave */
     if (const char *er = getenv("NTG_B200_ROUNDS")) R = atoi(er); /* tuning experiments */
     if (R < 1) R = 1;
     if (R > 8) R = 8;
-    const size_t smem_cap = (size_t)(getenv("NTG_B200_SMEMCAP") ? atoi(getenv("NTG_B200_SMEMCAP")) : 100) * 1024;
+    const size_t smem_cap = (size_t)(getenv("NTG_B200_SMEMCAP") ? atoi(getenv("NTG_B200_SMEMCAP")) : (wide ? 200 : 100)) * 1024;
     while (R > 1 && SmallSmem{G * R, nbps, T.S, T.nout, T.nC, segtot}.bytes() > smem_cap) R--;
     SmallSmem lay{G * R, nbps, T.S, T.nout, T.nC, segtot};
     const size_t smem = lay.bytes();
@@ -887,7 +889,8 @@ int launch_eval_small(const ntgb_launch *L)
      * gather, so that the single-GPU instantiation carries none of their code */
     static const bool force_peers = getenv("NTG_B200_FORCE_PEERS_KERNEL") != nullptr; /* A/B: code shape vs NVLink */
     const bool push_ok = G * R <= block; /* one thread per pair of a tile */
-    auto kern = full ? (hot && (a.npeers == 0 || push_ok) ? ((a.npeers > 0 || force_peers) && push_ok ? ntg_eval_small_kernel<PK, true, true, true>
+    auto kern = wide ? (full ? ntg_eval_small_kernel<PK, true, false, true, 512> : ntg_eval_small_kernel<PK, false, false, true, 512>)
+              : full ? (hot && (a.npeers == 0 || push_ok) ? ((a.npeers > 0 || force_peers) && push_ok ? ntg_eval_small_kernel<PK, true, true, true>
                                              : ntg_eval_small_kernel<PK, true, true, false>)
                             : ntg_eval_small_kernel<PK, true, false, true>)
                      : ntg_eval_small_kernel<PK, false, false, true>;

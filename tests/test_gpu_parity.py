@@ -150,6 +150,29 @@ def test_general_kernel_on_small_shapes(torch_cuda, port, name, monkeypatch):
     pb.close()
 
 
+@pytest.mark.parametrize("nbps,P", [(257, 5), (320, 37), (512, 3)])
+@pytest.mark.parametrize("fast", [False, True], ids=["exact", "fast"])
+def test_wide_register_table_kernel(torch_cuda, port, nbps, P, fast, monkeypatch):
+    """257..512 breakpoints with outputs of DIFFERENT spline setups (no cluster kernel): K1s on CTAs of
+    512 threads, one per SM.  Same bar as everywhere (the endpoint callbacks use libm: 1e-12), plus
+    agreement with the general kernel K1 on the same inputs, and a ragged batch."""
+    spec = configs.endpoint(nbps, name=f"endpoint_{nbps}")
+    X = np.random.default_rng(nbps).uniform(-1, 1, (P, spec.nC))
+    o = port.eval(spec, X, dense=False)
+    pb, r = gpu_eval(torch_cuda, spec, X, fast, want_Z=True)
+    for k in ("f", "g", "c", "Jband"):
+        assert_close(r[k], o[k], f"endpoint_{nbps}.{k} (K1s, 512 threads)")
+    assert_close(r["result"][:, 0], o["f"], "result[:,0]")
+    assert_close(r["result"][:, 1], violation(spec, o["c"]), "result[:,1]")
+    pb.close()
+    monkeypatch.setenv("NTG_B200_KERNEL", "general")
+    pb, g = gpu_eval(torch_cuda, spec, X, fast, want_Z=True)
+    for k in ("f", "g", "c", "Jband"):
+        assert_close(r[k], g[k], f"endpoint_{nbps}.{k} K1s-512 vs K1")
+    assert_bitexact(r["Z"], g["Z"], "flat outputs, K1s-512 vs K1")
+    pb.close()
+
+
 @pytest.mark.parametrize("ninterv,P", [(200, 3), (150, 75), (300, 5), (640, 2)])
 @pytest.mark.parametrize("fast", [False, True], ids=["exact", "fast"])
 def test_cluster_kernel_long_horizons(torch_cuda, port, ninterv, P, fast):
@@ -398,7 +421,7 @@ def test_callback_abort_request(torch_cuda):
     pb.close()
 
 
-@pytest.mark.parametrize("case", ["k1s_endpoint", "k1s_kincar64", "k1_endpoint", "k1_syn6", "k1c_301", "k1c_601", "k1ch_301",
+@pytest.mark.parametrize("case", ["k1s_endpoint", "k1s_kincar64", "k1s_endpoint320", "k1_endpoint", "k1_syn6", "k1c_301", "k1c_601", "k1ch_301",
                                   "k1ch_300", "k1ch_601"])
 @pytest.mark.parametrize("jac", [JAC_BAND, JAC_DENSE], ids=["band", "dense"])
 def test_no_out_of_bounds_writes(torch_cuda, case, jac, monkeypatch):
@@ -409,6 +432,7 @@ def test_no_out_of_bounds_writes(torch_cuda, case, jac, monkeypatch):
     from ntg_b200 import Problem
     from ntg_b200.abi import NtgbEvalArgs
     spec, P = {"k1s_endpoint": (configs.endpoint(), 7), "k1s_kincar64": (configs.kincar(64), 9),
+               "k1s_endpoint320": (configs.endpoint(320, name="e320"), 5),
                "k1_endpoint": (configs.endpoint(), 7), "k1_syn6": (configs.syn6(12, name="s12"), 3),
                "k1c_301": (configs.syn6(150, name="s150"), 3), "k1c_601": (configs.syn6(300, name="s300"), 2),
                "k1ch_301": (configs.syn6(150, name="s150"), 3), "k1ch_300": (configs.syn6(150, nbps=300, name="s150e"), 4),

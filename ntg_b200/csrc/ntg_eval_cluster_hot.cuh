@@ -150,8 +150,7 @@ struct ClusterHotSmem {
     __host__ __device__ size_t violx_off() const { return viol_off() + 2; }                           /* u64 [2][cl] (rank 0): every rank's */
     __host__ __device__ size_t sc_off() const { return violx_off() + 2 * (size_t)cl; }                /* [2][2] cI, cF (rank 0) */
     __host__ __device__ size_t fall_off() const { return sc_off() + 4; }                              /* rank 0: [2][nbps]; others: [2][bpc] own integrand */
-    __host__ __device__ size_t t_off() const { return fall_off() + 2 * (size_t)nbps; }                /* [nbps] (rank 0) */
-    __host__ __device__ size_t dt_off() const { return t_off() + nbps; }                              /* [nbps]      */
+    __host__ __device__ size_t dt_off() const { return fall_off() + 2 * (size_t)nbps; }               /* [nbps]      */
     __host__ __device__ size_t wf_off() const { return dt_off() + nbps; }                             /* [nbps] node weights (fast variant) */
     __host__ __device__ size_t C_off() const { return wf_off() + nbps; }                              /* [cwin]      */
     __host__ __device__ size_t bar_off() const { return C_off() + cwin; }                             /* u64 [2*nst + 4] full, empty, ready[2], free[2] */
@@ -219,7 +218,6 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int cwi
     unsigned long long *violx_s = reinterpret_cast<unsigned long long *>(smem + L.violx_off()); /* rank 0: [2][CL] */
     double *sc_s = smem + L.sc_off();     /* rank 0: [buf][0] initial cost, [buf][1] final cost */
     double *fall_s = smem + L.fall_off(); /* rank 0: the integrand of ALL breakpoints [buf][nbps]; else this CTA's [buf][bpc] */
-    double *t_s = smem + L.t_off();       /* rank 0: trapezoid terms of the scalar cost */
     double *dt_s = smem + L.dt_off();
     double *wf_s = smem + L.wf_off();     /* (dt[n-1] + dt[n])/2: the trapezoid rule as node weights */
     double *C_s = smem + L.C_off();
@@ -399,16 +397,25 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int cwi
             } else {
                 if (CL > 1) mbar_wait_cluster(ready_a + 8u * (unsigned)buf, use & 1u);
                 /* IntegrateVector TRAPEZOID (src/integrator.c:21-24): a sequential chain over all breakpoints */
-                const double *fp = fall_s + (size_t)buf * nbps;
+                double *fp = fall_s + (size_t)buf * nbps;
                 if (doU) {
-                    for (int i = lane; i < nbps - 1; i += 32) t_s[i] = (dt_s[i] * (fp[i + 1] + fp[i])) / 2;
+                    /* the trapezoid terms overwrite the integrand in place (term i needs f[i] and f[i+1]: 32 at a
+                     * time in ascending order, every lane reads before any lane writes) -- a separate array of
+                     * nbps terms was the 3 KB that kept a fourth ring stage out of shared memory */
+                    for (int base = 0; base < nbps - 1; base += 32) {
+                        const int i = base + lane;
+                        double a = 0.0, b = 0.0;
+                        if (i < nbps - 1) { a = fp[i]; b = fp[i + 1]; }
+                        __syncwarp();
+                        if (i < nbps - 1) fp[i] = (dt_s[i] * (b + a)) / 2;
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) {
                     double In = 0.0;
                     if (doU) {
 #pragma unroll 8
-                        for (int i = 0; i < nbps - 1; i++) In = In + t_s[i];
+                        for (int i = 0; i < nbps - 1; i++) In = In + fp[i];
                     }
                     unsigned long long vb = viol_s[buf];
                     viol_s[buf] = 0ull;
@@ -767,6 +774,9 @@ int launch_eval_cluster_hot(const ntgb_launch *L)
         }
         const size_t smem = lay.bytes();
         if (smem > (size_t)L->max_smem_optin) return -1001;
+        if (getenv("NTG_B200_DEBUG"))
+            fprintf(stderr, "K1c/H: CL %d bpc %d halo %d stages %d x %zu B (of %d per problem and CTA) plan in smem %d (%d entries) cwin %d smem %zu\n",
+                    CL, bpc, H, lay.nst, lay.stage_doubles() * 8, NS, plan_smem, plan_share, T.plan_cwin, smem);
         static const bool force_peers = getenv("NTG_B200_FORCE_PEERS_KERNEL") != nullptr; /* A/B: code shape vs NVLink */
         auto kern = (a.npeers > 0 || force_peers) ? ntg_eval_cluster_hot_kernel<PK, true> : ntg_eval_cluster_hot_kernel<PK, false>;
         cudaError_t e = raise_smem_limit((const void *)kern, L->max_smem_optin);

@@ -233,6 +233,20 @@ int  ntgb_eval_linear(ntgb_problem *pb, int P, const double *C, double *lin,
 
 /* Batched SplineInterp (reference src/colloc.c:449-484): for every problem p
  * and time t[i], out[(p*nt + i)*nz + iz_j + d].  Device pointers. */
+/*
+ * Batched IntegrateVector / IntegrateFMatrixCols (/root/reference/src/integrator.c:16-62) with the
+ * reference's three rules (src/integrator.h:19-21).  f holds nchain sample vectors of n values
+ * ([nchain][n], e.g. nchain = P columns), t the n sample times; I[q] = the rule's sum over vector q,
+ * accumulated in the reference's order with the reference's expression (bit-identical to it).  The
+ * evaluator itself only ever integrates with TRAPEZOID, as every call site of the reference does
+ * (src/cost.c:61,96,111,134); the other two rules are here for callers of the public helper.
+ * Device pointers; runs on the current device.
+ */
+#define NTGB_QUAD_FEULER    0
+#define NTGB_QUAD_BEULER    1
+#define NTGB_QUAD_TRAPEZOID 2
+int  ntgb_integrate(int rule, long long nchain, int n, const double *f, const double *t, double *I, void *stream);
+
 int  ntgb_spline_interp(ntgb_problem *pb, int P, const double *C, int nt,
                         const double *t, double *out, void *stream);
 

@@ -862,6 +862,23 @@ int alm_prepare(ntgb_problem *pb)
     return 0;
 }
 
+/* IntegrateVector / IntegrateFMatrixCols (src/integrator.c:16-62) for a batch: one thread per (problem,
+ * column) walks its n samples in the reference's order, with the reference's expression per rule */
+__global__ void k_integrate(int rule, long long nchain, int n, const double *f, const double *t, double *I)
+{
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nchain) return;
+    const double *fq = f + q * n;
+    double acc = 0.0;
+    if (rule == NTGB_QUAD_TRAPEZOID)
+        for (int i = 0; i < n - 1; i++) acc += (t[i + 1] - t[i]) * (fq[i + 1] + fq[i]) / 2;
+    else if (rule == NTGB_QUAD_FEULER)
+        for (int i = 0; i < n - 1; i++) acc += (t[i + 1] - t[i]) * fq[i];
+    else
+        for (int i = 0; i < n - 1; i++) acc += (t[i + 1] - t[i]) * fq[i + 1];
+    I[q] = acc;
+}
+
 /* ---- ntgb_solve_sqp: one CTA per problem runs ntg_sqp.cuh's sqp_step in shared memory ---------- */
 namespace sqp = ntgb::sqp;
 
@@ -2476,6 +2493,16 @@ int ntgb_peer_table_free(ntgb_problem *pb, double *table)
     if (!pb || !table) return 0;
     DeviceGuard dg(pb->device);
     CUDA_TRY(cudaFree(table));
+    return 0;
+}
+
+int ntgb_integrate(int rule, long long nchain, int n, const double *f, const double *t, double *I, void *stream)
+{
+    if (rule != NTGB_QUAD_FEULER && rule != NTGB_QUAD_BEULER && rule != NTGB_QUAD_TRAPEZOID)
+        return fail(NTGB_EINVAL, "ntgb_integrate: unknown rule %d", rule);
+    if (nchain <= 0) return 0;
+    if (!f || !t || !I || n < 1) return fail(NTGB_EINVAL, "ntgb_integrate: null argument or n < 1");
+    CUDA_TRY(launch(k_integrate, (unsigned)((nchain + 127) / 128), 128, (cudaStream_t)stream, rule, nchain, n, f, t, I));
     return 0;
 }
 

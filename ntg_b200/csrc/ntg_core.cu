@@ -959,20 +959,23 @@ __global__ void k_sqp_step(int P, ntgb_devtab T, SqpDesc D, SqpArrays S, const d
         for (int e = 0; e < nC; e++) a += D.N[(size_t)k * nC + e] * gp[e];
         gr[k] = a;
     }
+    for (int i = tid; i < m; i += nt)
+        hrow[i] = i < n_li ? lin[(size_t)p * D.nclin + D.li_idx[i]] : c[(size_t)p * D.ncnln + (i - n_li)];
+    /* reduced row gradients, one row per thread and step.  Nonlinear row r of the band-compact Jacobian
+     * (include/ntg_b200.h): slot jk0[j] + k of output j holds the derivative with respect to coefficient
+     * iC[j] + offset + k.  The band values are fetched EIGHT at a time before they are used: behind the
+     * shared-memory updates the compiler cannot move a global load, and one exposed load latency per
+     * slot was 14 % of the kernel. */
+    const double *Jp = J + (size_t)p * T.ncnln * T.S;
     for (int i = tid; i < m; i += nt) {
         double *Ai = w.A + (size_t)i * ld;
         if (i < n_li) {
-            hrow[i] = lin[(size_t)p * D.nclin + D.li_idx[i]];
             for (int k = 0; k < nr; k++) Ai[k] = D.ArN[(size_t)i * nr + k];
             continue;
         }
-        /* nonlinear row r of the band-compact Jacobian (include/ntg_b200.h): slot jk0[j] + k of
-         * output j holds the derivative with respect to coefficient iC[j] + offset + k */
         const int r = i - n_li;
-        hrow[i] = c[(size_t)p * D.ncnln + r];
         for (int k = 0; k < nr; k++) Ai[k] = 0.0;
-        const double *Jp = J + (size_t)p * T.ncnln * T.S;
-        int kind, mm = 0, bp = 0, rr = r; /* 0 initial (src/colloc.c:254: columns from iC_j), 1 trajectory, 2 final */
+        int kind, mm = 0, bp = 0; /* 0 initial (src/colloc.c:254: columns from iC_j), 1 trajectory, 2 final */
         if (r < T.nnlic) kind = 0;
         else if (r < T.nnlic + T.nnltc * T.nbps) {
             kind = 1;
@@ -985,12 +988,26 @@ __global__ void k_sqp_step(int P, ntgb_devtab T, SqpDesc D, SqpArrays S, const d
         for (int j = 0; j < T.nout; j++) {
             const int ord = T.order[j], s0 = T.jk0[j];
             const int col0 = T.iC[j] + (kind == 0 ? 0 : T.off[j][bp]);
-            for (int k = 0; k < ord; k++) {
-                const double v = kind == 1 ? Jp[ntgb_band_index(T.nnlic, T.nnltc, T.S, T.nbps, T.band_tile, mm, s0 + k, bp)]
-                                           : Jp[(size_t)rr * T.S + s0 + k];
-                if (v == 0.0) continue;
-                const double *Nc = D.N + (col0 + k);
-                for (int q = 0; q < nr; q++) Ai[q] += v * Nc[(size_t)q * nC];
+            const double *Jr;
+            size_t stride;
+            if (kind == 1) {
+                const int t = bp / T.band_tile;
+                Jr = Jp + ntgb_band_index(T.nnlic, T.nnltc, T.S, T.nbps, T.band_tile, mm, s0, bp);
+                stride = (size_t)(T.nbps - t * T.band_tile < T.band_tile ? T.nbps - t * T.band_tile : T.band_tile);
+            } else {
+                Jr = Jp + (size_t)r * T.S + s0;
+                stride = 1;
+            }
+            for (int k0 = 0; k0 < ord; k0 += 8) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) v[u] = k0 + u < ord ? __ldg(Jr + (size_t)(k0 + u) * stride) : 0.0;
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    if (v[u] == 0.0) continue;
+                    const double *Nc = D.N + (col0 + k0 + u);
+                    for (int q = 0; q < nr; q++) Ai[q] += v[u] * Nc[(size_t)q * nC];
+                }
             }
         }
     }

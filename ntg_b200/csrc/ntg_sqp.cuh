@@ -54,6 +54,60 @@ struct Coop {
         __syncwarp();
 #endif
     }
+    /* sum / maximum over the group, result in every thread; EVERY thread must call it.  red: [nt / 32]
+     * doubles of shared scratch (only touched by groups of more than one warp).  Fixed tree: deterministic. */
+    template <bool MAX>
+    NTG_HD double reduce(double v, double *red) const
+    {
+#ifdef __CUDA_ARCH__
+        for (int d = 16; d > 0; d >>= 1) {
+            const double o = __shfl_xor_sync(0xffffffffu, v, d);
+            v = MAX ? fmax(v, o) : v + o;
+        }
+        if (nt > 32) {
+            __syncthreads();
+            if (lane == 0) red[tid >> 5] = v;
+            __syncthreads();
+            v = red[0];
+            for (int k = 1; k < (nt >> 5); k++) v = MAX ? fmax(v, red[k]) : v + red[k];
+        }
+#else
+        (void)red;
+#endif
+        return v;
+    }
+    /* (largest key, smallest index among equals) over the group; idx < 0 = no candidate */
+    NTG_HD void argmax(double &key, int &idx, double *red, int *redi) const
+    {
+#ifdef __CUDA_ARCH__
+        for (int d = 16; d > 0; d >>= 1) {
+            const double ok = __shfl_xor_sync(0xffffffffu, key, d);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, d);
+            if (oi >= 0 && (idx < 0 || ok > key || (ok == key && oi < idx))) {
+                key = ok;
+                idx = oi;
+            }
+        }
+        if (nt > 32) {
+            __syncthreads();
+            if (lane == 0) {
+                red[tid >> 5] = key;
+                redi[tid >> 5] = idx;
+            }
+            __syncthreads();
+            key = red[0];
+            idx = redi[0];
+            for (int k = 1; k < (nt >> 5); k++)
+                if (redi[k] >= 0 && (idx < 0 || red[k] > key || (red[k] == key && redi[k] < idx))) {
+                    key = red[k];
+                    idx = redi[k];
+                }
+        }
+#else
+        (void)red;
+        (void)redi;
+#endif
+    }
 };
 
 /* work space of one QP (all in shared memory on the GPU) */
@@ -231,17 +285,9 @@ NTG_HD int gi_solve(const C &cg, const Qp &w, const double *L, const double *g0)
                 bi = i;
             }
         }
-        w.red[cg.tid] = bkey;
-        w.redi[cg.tid] = bi;
-        cg.sync();
+        cg.argmax(bkey, bi, w.red, w.redi);
         if (cg.tid == 0) {
-            double k0 = tol;
-            int i0 = -1;
-            for (int t = 0; t < cg.nt; t++)
-                if (w.redi[t] >= 0 && (w.red[t] > k0 || (w.red[t] == k0 && w.redi[t] < i0))) {
-                    k0 = w.red[t];
-                    i0 = w.redi[t];
-                }
+            const int i0 = bi;
             w.shi[0] = i0;
             if (i0 >= 0) {
                 double ax = 0.0;
@@ -332,16 +378,26 @@ NTG_HD int gi_solve(const C &cg, const Qp &w, const double *L, const double *g0)
             if (cg.tid == 0) w.u[q] += t;
             cg.sync();
             if (code == 3) { /* the full step: the row joins the active set */
+                /* Givens rotations that fold d[q+1:] into d[q], back to front: the value carried into the
+                 * rotation of (j-1, j) is the norm of d[j:], so every pair (c, s) follows from the suffix sums
+                 * of squares -- one short chain of additions, then one sqrt and two divisions PER THREAD
+                 * instead of a chain of hypot() calls on one thread */
                 if (cg.tid == 0) {
-                    for (int j = n - 1; j > q; j--) {
-                        const double a = w.dv[j - 1], b = w.dv[j];
-                        const double h = hypot(a, b);
-                        w.cs[j] = h == 0.0 ? 1.0 : a / h;
-                        w.sn[j] = h == 0.0 ? 0.0 : b / h;
-                        w.dv[j - 1] = h == 0.0 ? a : h;
-                        w.dv[j] = 0.0;
+                    double ss = 0.0;
+                    for (int j = n - 1; j >= q; j--) {
+                        ss += w.dv[j] * w.dv[j];
+                        w.z[j] = ss; /* z is free again: x has been updated */
                     }
-                    for (int k = 0; k <= q; k++) w.Rm[k * ld + q] = w.dv[k];
+                }
+                cg.sync();
+                for (int j = q + 1 + cg.tid; j < n; j += cg.nt) {
+                    const double h = sqrt(w.z[j - 1]);
+                    w.cs[j] = h == 0.0 ? 1.0 : w.dv[j - 1] / h;
+                    w.sn[j] = h == 0.0 ? 0.0 : (j == n - 1 ? w.dv[j] : sqrt(w.z[j])) / h; /* the last entry keeps its sign */
+                }
+                if (cg.tid == 0) {
+                    for (int k = 0; k < q; k++) w.Rm[k * ld + q] = w.dv[k];
+                    w.Rm[q * ld + q] = n - 1 > q ? sqrt(w.z[q]) : w.dv[q];
                     w.act[q] = sg > 0 ? ip + 1 : -(ip + 1);
                     w.state[ip] = w.bl[ip] == w.bu[ip] ? 3 : (sg > 0 ? 1 : 2);
                 }
@@ -571,27 +627,36 @@ NTG_HD void sqp_step(const C &cg, const Qp &w, const StepState &S, const StepOpt
         Ad[i] = a;
     }
     cg.sync();
+    double kkt = 0.0, dmax = 0.0, gd = 0.0, dBd = 0.0;
+    for (int k = cg.tid; k < n; k += cg.nt) {
+        kkt = fmax(kkt, fabs(grL[k]));
+        dmax = fmax(dmax, fabs(w.x[k]));
+        gd += gr[k] * w.x[k];
+        dBd += w.x[k] * Bs[k];
+    }
+    double vmax = 0.0, vsum = 0.0, almax = 0.0, dsum = 0.0, nactd = 0.0;
+    for (int i = cg.tid; i < m; i += cg.nt) {
+        const bool vl = w.bl[i] > -kBig && w.bl[i] > 0.0, vu = w.bu[i] < kBig && w.bu[i] < 0.0;
+        const double v = vl ? w.bl[i] : (vu ? -w.bu[i] : 0.0);
+        const double sc = fmax(1.0, fmax(fabs(hl[i]) < kBig ? fabs(hl[i]) : 0.0, fabs(hu[i]) < kBig ? fabs(hu[i]) : 0.0));
+        vmax = fmax(vmax, v / sc);
+        vsum += v;
+        almax = fmax(almax, fabs(w.lam[i]));
+        if (vl) dsum -= Ad[i];
+        else if (vu) dsum += Ad[i];
+        nactd += w.state[i] != 0 ? 1.0 : 0.0;
+    }
+    kkt = cg.template reduce<true>(kkt, w.red);
+    dmax = cg.template reduce<true>(dmax, w.red);
+    gd = cg.template reduce<false>(gd, w.red);
+    dBd = cg.template reduce<false>(dBd, w.red);
+    vmax = cg.template reduce<true>(vmax, w.red);
+    vsum = cg.template reduce<false>(vsum, w.red);
+    almax = cg.template reduce<true>(almax, w.red);
+    dsum = cg.template reduce<false>(dsum, w.red);
+    nactd = cg.template reduce<false>(nactd, w.red);
     if (cg.tid == 0) {
-        double kkt = 0.0, dmax = 0.0, gd = 0.0, dBd = 0.0;
-        for (int k = 0; k < n; k++) {
-            kkt = fmax(kkt, fabs(grL[k]));
-            dmax = fmax(dmax, fabs(w.x[k]));
-            gd += gr[k] * w.x[k];
-            dBd += w.x[k] * Bs[k];
-        }
-        double vmax = 0.0, vsum = 0.0, almax = 0.0, dsum = 0.0;
-        int nact = 0;
-        for (int i = 0; i < m; i++) {
-            const bool vl = w.bl[i] > -kBig && w.bl[i] > 0.0, vu = w.bu[i] < kBig && w.bu[i] < 0.0;
-            const double v = vl ? w.bl[i] : (vu ? -w.bu[i] : 0.0);
-            const double sc = fmax(1.0, fmax(fabs(hl[i]) < kBig ? fabs(hl[i]) : 0.0, fabs(hu[i]) < kBig ? fabs(hu[i]) : 0.0));
-            vmax = fmax(vmax, v / sc);
-            vsum += v;
-            almax = fmax(almax, fabs(w.lam[i]));
-            if (vl) dsum -= Ad[i];
-            else if (vu) dsum += Ad[i];
-            nact += w.state[i] != 0;
-        }
+        const int nact = (int)nactd;
         int status = 0;
         if (vmax <= o.ctol && kkt <= o.gtol * fmax(1.0, fabs(f)) && !restor) status = 1;
         else if (restor && dmax < 1e-12) status = 4;

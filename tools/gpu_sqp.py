@@ -17,7 +17,7 @@ P = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 spec = _kincar_active_constraints()
 X = configs.coefficients("cfg3", P, spec, seed=5)
 pb = Problem(spec, 0, fast=True)
-for name in ("sqp", "nlp"):
+for name in (sys.argv[2].split(",") if len(sys.argv) > 2 else ("sqp", "nlp")):
     fn = pb.solve_sqp if name == "sqp" else pb.solve_nlp
     fn(torch.from_numpy(X[:256]).cuda())
     Cd = torch.from_numpy(X).cuda()

@@ -1366,8 +1366,9 @@ int ntgb_create(ntgb_problem **out, const ntgb_setup *s, int device)
         T.col_lo = dlo; T.col_hi = dhi;
         /* runs of equal offset per output, and the run each column's gather starts in */
         std::vector<int> seg0(T.nC, 0);
+        std::vector<std::vector<int>> runs_st((size_t)nout), runs_so((size_t)nout);
         for (int j = 0; j < nout; j++) {
-            std::vector<int> st, so;
+            std::vector<int> &st = runs_st[j], &so = runs_so[j];
             for (int bp = 0; bp < nbps; bp++) {
                 const int o = pb->hoff[(size_t)j * nbps + bp];
                 if (bp == 0 || o != so.back()) { st.push_back(bp); so.push_back(o); }
@@ -1392,11 +1393,15 @@ int ntgb_create(ntgb_problem **out, const ntgb_setup *s, int device)
         T.col_seg0 = dseg0;
 
         /* K1s quadrature schedule (ntg_kernel_args.h): longest-chain-first packing of the nC+1
-         * chains into the slots a 256-thread CTA has for GR = G*(r+1) problems per tile */
-        T.sched_G = 0;
+         * chains into NS slots, one table per NS = 1 .. sched_maxns (a 256-thread CTA whose largest
+         * tile has n problems runs NS = min(256 / n, sched_maxns) slots of n lanes) */
+        T.sched_maxns = 0;
         T.sched = nullptr;
+        T.img_w = nullptr;
+        T.img_i = nullptr;
         if (nbps <= NTGB_SCHED_BLOCK) {
-            const int G0 = NTGB_SCHED_BLOCK / nbps, ncol = T.nC + 1, stride = NTGB_SCHED_BLOCK + 1 + ncol;
+            const int ncol = T.nC + 1, stride = NTGB_SCHED_BLOCK + 1 + ncol;
+            const int maxns = ncol < NTGB_SCHED_MAXNS ? ncol : NTGB_SCHED_MAXNS;
             std::vector<int> len((size_t)ncol), order((size_t)ncol);
             for (int c = 0; c < T.nC; c++) {
                 const int i0 = lo[c] > 0 ? lo[c] - 1 : 0;
@@ -1406,13 +1411,8 @@ int ntgb_create(ntgb_problem **out, const ntgb_setup *s, int device)
             len[T.nC] = nbps - 1;
             for (int c = 0; c < ncol; c++) order[c] = c;
             std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return len[a] > len[b]; });
-            std::vector<int> sched((size_t)8 * stride, 0);
-            for (int r = 0; r < 8; r++) {
-                const int GR = G0 * (r + 1);
-                const int lanes = GR < NTGB_SCHED_BLOCK ? GR : NTGB_SCHED_BLOCK;
-                int NS = NTGB_SCHED_BLOCK / lanes;
-                if (NS > ncol) NS = ncol;
-                T.sched_ns[r] = NS;
+            std::vector<int> sched((size_t)maxns * stride, 0);
+            for (int NS = 1; NS <= maxns; NS++) {
                 std::vector<long long> load((size_t)NS, 0);
                 std::vector<std::vector<int>> lists((size_t)NS);
                 for (int c : order) {
@@ -1422,7 +1422,7 @@ int ntgb_create(ntgb_problem **out, const ntgb_setup *s, int device)
                     load[best] += len[c] + 4; /* + a fixed cost per chain */
                     lists[best].push_back(c);
                 }
-                int *st = &sched[(size_t)r * stride], *cols = st + NTGB_SCHED_BLOCK + 1, pos = 0;
+                int *st = &sched[(size_t)(NS - 1) * stride], *cols = st + NTGB_SCHED_BLOCK + 1, pos = 0;
                 for (int q = 0; q < NS; q++) {
                     st[q] = pos;
                     for (int c : lists[q]) cols[pos++] = c;
@@ -1432,7 +1432,81 @@ int ntgb_create(ntgb_problem **out, const ntgb_setup *s, int device)
             int *dsched = nullptr;
             if ((rc = dev_upload(pb, &dsched, sched.data(), sched.size()))) return rc;
             T.sched = dsched;
-            T.sched_G = G0;
+            T.sched_maxns = maxns;
+
+            /* K1s steady-state image (ntg_kernel_args.h): what the kernel's prologue would build for
+             * funobj mode 2 + funcon mode 2, in the layout of its shared memory (ntg_eval_small.cuh:
+             * SmallSmem::pitch, the weights, the run tables, the chain description per column) */
+            int pitch = (nbps + 1) & ~1;
+            if (((pitch >> 1) & 1) == 0) pitch += 2;
+            std::vector<double> imgw((size_t)2 * (pitch + 2), 0.0);
+            for (int n = 0; n < pitch + 2; n++) {
+                const double *b = pb->bps.data();
+                const double lo_w = (n >= 1 && n < nbps) ? (b[n] - b[n - 1]) * 0.5 : 0.0;
+                const double hi_w = (n + 1 < nbps) ? (b[n + 1] - b[n]) * 0.5 : 0.0;
+                imgw[n] = (n >= 1 && n < nbps) ? b[n] - b[n - 1] : 0.0;
+                imgw[(size_t)pitch + 2 + n] = lo_w + hi_w;
+            }
+            int segtot = 0;
+            for (int j = 0; j < nout; j++) segtot += T.nseg[j] + 1;
+            const int par0 = 2 * segtot + 4;
+            std::vector<int> imgi((size_t)par0 + (size_t)ncol * 9, 0);
+            {
+                int base = 0;
+                for (int j = 0; j < nout; j++) {
+                    for (int i = 0; i <= T.nseg[j]; i++) {
+                        imgi[(size_t)base + i] = runs_st[j][i];
+                        imgi[(size_t)segtot + base + i] = runs_so[j][i];
+                    }
+                    base += T.nseg[j] + 1;
+                }
+            }
+            imgi[(size_t)2 * segtot + 0] = 0;
+            imgi[(size_t)2 * segtot + 1] = nbps;
+            imgi[(size_t)2 * segtot + 2] = 0;
+            const bool doI = T.nicf != 0, doU = T.nucf != 0, doF = T.nfcf != 0;
+            for (int c = 0; c <= T.nC; c++) {
+                int *pp = &imgi[(size_t)par0 + (size_t)c * 9];
+                if (c == T.nC) {
+                    pp[1] = doU ? nbps - 1 : 0;
+                    pp[3] = 2 * segtot;
+                    pp[8] = 2 * segtot + 2;
+                    pp[4] = T.S * pitch; /* x (problems per tile) in the kernel: f_s follows D_s */
+                    pp[5] = 1;
+                    continue;
+                }
+                int sb = 0;
+                for (int j = 0; j < nout; j++) {
+                    const int clj = c - T.iC[j];
+                    if (clj >= 0 && clj < T.ncoef[j]) {
+                        const int ord = T.order[j];
+                        if (doU) {
+                            pp[0] = lo[c] > 0 ? lo[c] - 1 : 0;
+                            pp[1] = (hi[c] < nbps - 2 ? hi[c] : nbps - 2) + 1;
+                            pp[2] = seg0[c];
+                        }
+                        pp[3] = sb;
+                        pp[8] = segtot + sb;
+                        pp[4] = T.jk0[j] * pitch;
+                        pp[5] = ord;
+                        pp[6] = clj;
+                        int iDI = 0, iDF = 0;
+                        if (doI && clj < ord) iDI = T.jk0[j] + clj + 1;
+                        if (doF) {
+                            const int k = clj - runs_so[j][(size_t)T.nseg[j] - 1];
+                            if (k >= 0 && k < ord) iDF = T.jk0[j] + k + 1;
+                        }
+                        pp[7] = iDI | (iDF << 16);
+                    }
+                    sb += T.nseg[j] + 1;
+                }
+            }
+            double *dimgw = nullptr;
+            int *dimgi = nullptr;
+            if ((rc = dev_upload(pb, &dimgw, imgw.data(), imgw.size()))) return rc;
+            if ((rc = dev_upload(pb, &dimgi, imgi.data(), imgi.size()))) return rc;
+            T.img_w = dimgw;
+            T.img_i = dimgi;
         }
 
     }

@@ -322,13 +322,16 @@ __device__ __noinline__ void push_pairs(const double *res_s, double2 *const *dst
  * in band layout, f / g / c / J all requested, Z not requested. */
 template <class PK, bool FULL, bool HOT = false, bool PEERS = true, int BLOCK = 256>
 __global__ void __launch_bounds__(BLOCK, 512 / BLOCK)
-ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R, int segtot, int pdl)
+ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R, int segtot, int flags)
 {
     constexpr int NOUT = PK::kNout;
     constexpr int NZ = pk_nz<PK>();
     constexpr int NB = pk_tab_doubles<PK>();
     extern __shared__ double smem[];
-    const int GR = G * R;
+    /* flags: bit 0 programmatic dependent launch, bit 1 rotate the peer-store order, bits 4-7 tiles per
+     * CTA of an EVEN split (0: tiles of G*R problems dealt round-robin), bits 8.. rows of a tile's
+     * buffers in an even split (>= the largest tile; G*R otherwise) */
+    const int GR = (flags >> 8) ? (flags >> 8) : G * R;
     const SmallSmem L{GR, T.nbps, T.S, T.nout, T.nC, segtot};
     const int nbps = T.nbps, pitch = L.pitch(), nC = T.nC, P = A.P, S = T.S;
     double *D_s = smem + L.D_off();
@@ -358,7 +361,13 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
     if constexpr (PUSH) { /* destination tables: [local,] rank 0, rank 1, ... offset to this rank's first row */
         const int t = (int)threadIdx.x, loc = A.result != nullptr ? 1 : 0;
         if (t == 0 && loc) dst_s[0] = reinterpret_cast<double2 *>(A.result);
-        if (t < A.npeers) dst_s[loc + t] = reinterpret_cast<double2 *>(A.peer_result[t]) + A.peer_row0;
+        /* every CTA starts its round over the ranks at a different one (flags bit 1): 8 ranks x 296 CTAs
+         * that all store to rank 0 first, then rank 1, ... would take turns on one NVLink port at a time */
+        const int rot = (flags & 2) ? (int)(blockIdx.x % (unsigned)A.npeers) : 0;
+        if (t < A.npeers) {
+            const int src = t + rot < A.npeers ? t + rot : t + rot - A.npeers;
+            dst_s[loc + t] = reinterpret_cast<double2 *>(A.peer_result[src]) + A.peer_row0;
+        }
     }
 
     const int mode_obj = HOT ? 2 : A.mode_obj, mode_con = HOT ? 2 : A.mode_con;
@@ -379,22 +388,35 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
 
     /* the first tile's coefficients are requested before anything else: small batches are one tile
      * per CTA and this latency would otherwise sit behind the table loads below */
-    const int ntiles = (P + GR - 1) / GR;
-    const int tileC = GR * nC; /* doubles of coefficients per tile (contiguous in global memory) */
+    /* tiles: GR problems each, dealt round-robin to the CTAs -- or, for a batch of a few tiles per CTA
+     * (launch_eval_small), an EVEN split: every CTA gets the same number of tiles and the problems are
+     * split evenly over the tiles (tq or tq + 1 each).  Whole tiles of GR leave a third of the CTA
+     * slots empty at CFG-3 and put three full rounds on the others; 8192 lane changes are 683 tiles
+     * of 12, three for some CTAs and two for the rest */
+    const int ktiles = (flags >> 4) & 15;
+    const bool even = ktiles != 0;
+    const int ntiles = even ? ktiles * (int)gridDim.x : (P + GR - 1) / GR;
+    const int tq = even ? P / ntiles : GR, trem = even ? P - tq * ntiles : 0;
+    auto tile_p0 = [&](int tile) { return tile * tq + (tile < trem ? tile : trem); };
+    auto tile_np = [&](int tile, int p0) {
+        const int n = tq + (tile < trem ? 1 : 0);
+        return p0 + n > P ? P - p0 : n;
+    };
+    const int tileC = GR * nC; /* doubles of coefficients a tile's buffer holds (contiguous in global memory) */
     auto stage_C = [&](int tile, int buf) {
-        const long long first = (long long)tile * tileC;
-        const long long total = (long long)P * nC;
-        for (int e = threadIdx.x; e < tileC; e += blockDim.x)
-            if (first + e < total) cp_async8(C_s + (size_t)buf * tileC + e, A.C + first + e);
+        const int q0 = tile_p0(tile);
+        const int cnt = tile_np(tile, q0) * nC;
+        const double *src = A.C + (long long)q0 * nC;
+        for (int e = threadIdx.x; e < cnt; e += blockDim.x) cp_async8(C_s + (size_t)buf * tileC + e, src + e);
         cp_async_commit();
     };
     int buf = 0;
-    /* pdl: launched with programmatic stream serialization -- this grid may start while the grid in
+    /* flags bit 0: launched with programmatic stream serialization -- this grid may start while the grid in
      * front of it in the stream is still running.  Everything up to griddepcontrol.wait only reads
      * the batch-shared tables (written once at create time), so the whole prologue overlaps the
      * previous launch; coefficients are read and results written after the wait.  The grid behind
      * this one may start its own prologue as soon as every CTA of this grid is resident. */
-    if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (flags & 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     else if ((int)blockIdx.x < ntiles) stage_C(blockIdx.x, 0);
 
     /* ---- once per CTA: dt, offset runs, accumulators; once per thread: its table slice ----
@@ -408,6 +430,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
     const int cls = (bp == 0 ? 1 : 0) | (bp == nbps - 1 ? 2 : 0);
     double Bt[NB > 0 ? NB : 1];
     int offj[NOUT];
+#ifndef NTG_BT_LATE
     static_for<0, NOUT>([&](auto jc) {
         constexpr int j = decltype(jc)::value;
         constexpr int MD = PK::md(j);
@@ -420,25 +443,45 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
             for (int d = 0; d < MD; d++)
                 Bt[TB + k * MD + d] = (active && k < order) ? __ldg(T.Bt[j] + (size_t)(k * MD + d) * nbps + bp) : 0.0;
     });
+#endif
     const int bdim = (int)blockDim.x;
     auto rot = [&](int off) { const int t = (int)threadIdx.x - off; return t < 0 ? t + bdim : t; };
     const int tw = (int)threadIdx.x;                                   /* weights: from warp 0      */
     const int ts = rot(bdim >= 128 ? 96 : 0);                          /* run tables: from warp 3   */
     const int tc = rot(bdim >= 256 ? 128 : (bdim >= 128 ? 64 : 0));    /* chain table: from warp 4  */
-    for (int n = tw; n < pitch + 2; n += bdim) {
-        const double lo = (n >= 1 && n < nbps) ? (__ldg(T.bps + n) - __ldg(T.bps + n - 1)) * 0.5 : 0.0;
-        const double hi = (n + 1 < nbps) ? (__ldg(T.bps + n + 1) - __ldg(T.bps + n)) * 0.5 : 0.0;
-        wt_s[n] = (n >= 1 && n < nbps) ? __ldg(T.bps + n) - __ldg(T.bps + n - 1) : 0.0;
-        Wf_s[n] = lo + hi;
-    }
-    {
-        int base = 0;
-        for (int j = 0; j < T.nout; j++) {
-            for (int i = ts; i <= T.nseg[j]; i += bdim) {
-                segstart_s[base + i] = __ldg(T.seg_start[j] + i);
-                segoff_s[base + i] = __ldg(T.seg_off[j] + i);
+    /* steady state: the tile-invariant tables below were laid out once at create time in exactly the
+     * shape they have in shared memory (T.img_w, T.img_i; ntg_core.cu) -- the CTA copies them instead
+     * of building them: the building code is ~700 of the ~1100 instructions this prologue issues per
+     * warp, which a batch of one tile per CTA pays on its critical path */
+    bool use_img = false;
+    if constexpr (HOT)
+        use_img = T.img_i != nullptr && (PK::cb_ucf != nullptr || T.nucf == 0) && (PK::cb_icf != nullptr || T.nicf == 0) &&
+                  (PK::cb_fcf != nullptr || T.nfcf == 0);
+    if (use_img) {
+        for (int n = tw; n < 2 * (pitch + 2); n += bdim) wt_s[n] = __ldg(T.img_w + n);
+        const int par0 = 2 * segtot + 4, nimg = par0 + (nC + 1) * 9;
+        for (int i = ts; i < nimg; i += bdim) {
+            int v = __ldg(T.img_i + i);
+            const int r = i - par0;
+            if (r >= 0 && r % 9 == 4) v *= GR; /* a column's base inside D_s: (slot * pitch) * GR */
+            segstart_s[i] = v;
+        }
+    } else {
+        for (int n = tw; n < pitch + 2; n += bdim) {
+            const double lo = (n >= 1 && n < nbps) ? (__ldg(T.bps + n) - __ldg(T.bps + n - 1)) * 0.5 : 0.0;
+            const double hi = (n + 1 < nbps) ? (__ldg(T.bps + n + 1) - __ldg(T.bps + n)) * 0.5 : 0.0;
+            wt_s[n] = (n >= 1 && n < nbps) ? __ldg(T.bps + n) - __ldg(T.bps + n - 1) : 0.0;
+            Wf_s[n] = lo + hi;
+        }
+        {
+            int base = 0;
+            for (int j = 0; j < T.nout; j++) {
+                for (int i = ts; i <= T.nseg[j]; i += bdim) {
+                    segstart_s[base + i] = __ldg(T.seg_start[j] + i);
+                    segoff_s[base + i] = __ldg(T.seg_off[j] + i);
+                }
+                base += T.nseg[j] + 1;
             }
-            base += T.nseg[j] + 1;
         }
     }
     for (int q = threadIdx.x; q < GR; q += blockDim.x) {
@@ -448,15 +491,17 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
 
     /* phase-B mapping (tile-invariant): slot and problem lane of this thread, its column list */
     const bool want_g = HOT || (obj_d && A.g != nullptr);
-    const int lanesB = GR < (int)blockDim.x ? GR : (int)blockDim.x;
+    const int tmax = even ? tq + (trem ? 1 : 0) : GR; /* problems of the largest tile */
+    const int lanesB = tmax < (int)blockDim.x ? tmax : (int)blockDim.x;
     const int slotB = threadIdx.x / lanesB, laneB = threadIdx.x - slotB * lanesB;
-    const bool use_sched = T.sched != nullptr && blockDim.x == NTGB_SCHED_BLOCK && G == T.sched_G && R >= 1 && R <= 8;
-    const int *sched_st = use_sched ? T.sched + (size_t)(R - 1) * (NTGB_SCHED_BLOCK + 1 + nC + 1) : nullptr;
-    const int *sched_cols = use_sched ? sched_st + NTGB_SCHED_BLOCK + 1 : nullptr;
     const int NSB = (int)blockDim.x / lanesB;
+    const bool use_sched = T.sched != nullptr && blockDim.x == NTGB_SCHED_BLOCK;
+    const int NSS = NSB < T.sched_maxns ? NSB : T.sched_maxns; /* the schedule for this many slots */
+    const int *sched_st = use_sched ? T.sched + (size_t)(NSS - 1) * (NTGB_SCHED_BLOCK + 1 + nC + 1) : nullptr;
+    const int *sched_cols = use_sched ? sched_st + NTGB_SCHED_BLOCK + 1 : nullptr;
     int it0, it1, istep;
     if (use_sched) {
-        const bool has = slotB < T.sched_ns[R - 1];
+        const bool has = slotB < NSS;
         it0 = has ? __ldg(sched_st + slotB) : 0;
         it1 = has ? __ldg(sched_st + slotB + 1) : 0;
         istep = 1;
@@ -465,65 +510,84 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
         it1 = nC + 1;
         istep = NSB;
     }
-    if (threadIdx.x == 0) {
-        costseg_s[0] = 0;
-        costseg_s[1] = nbps;
-        costseg_s[2] = 0;
-    }
-    /* chain description per column, built once (everything in it is tile-invariant):
-     * [0] first breakpoint i0, [1] last term nend (no chain when i0 >= nend), [2] run holding i0,
-     * [3]/[8] where the output's run starts / run offsets sit in segstart_s, [4] the column's base
-     * inside D_s (doubles), [5] band width, [6] local column, [7] (slot in DI)+1 | ((slot in DF)+1)<<16 */
-    for (int c = tc; c <= nC; c += bdim) {
-        int *pp = par_s + c * 9;
-        if (c == nC) {
-            pp[0] = 0; pp[1] = (doU && obj_v) ? nbps - 1 : 0; pp[2] = 0; pp[3] = 2 * segtot; pp[8] = 2 * segtot + 2;
-            pp[4] = S * GR * pitch; /* f_s follows D_s */
-            pp[5] = 1; pp[6] = 0; pp[7] = 0;
-        } else {
-            int sb = 0;
-            pp[0] = 0; pp[1] = 0; pp[2] = 0; pp[3] = 0; pp[4] = 0; pp[5] = 0; pp[6] = 0; pp[7] = 0; pp[8] = 0;
-            for (int j = 0; j < T.nout; j++) {
-                const int clj = c - T.iC[j];
-                if (clj >= 0 && clj < T.ncoef[j]) {
-                    const int ord = T.order[j];
-                    if (doU) {
-                        const int lo = __ldg(T.col_lo + c), hi = __ldg(T.col_hi + c);
-                        pp[0] = lo > 0 ? lo - 1 : 0;
-                        pp[1] = (hi < nbps - 2 ? hi : nbps - 2) + 1;
-                        pp[2] = __ldg(T.col_seg0 + c);
+    if (!use_img) {
+        if (threadIdx.x == 0) {
+            costseg_s[0] = 0;
+            costseg_s[1] = nbps;
+            costseg_s[2] = 0;
+        }
+        /* chain description per column, built once (everything in it is tile-invariant):
+         * [0] first breakpoint i0, [1] last term nend (no chain when i0 >= nend), [2] run holding i0,
+         * [3]/[8] where the output's run starts / run offsets sit in segstart_s, [4] the column's base
+         * inside D_s (doubles), [5] band width, [6] local column, [7] (slot in DI)+1 | ((slot in DF)+1)<<16 */
+        for (int c = tc; c <= nC; c += bdim) {
+            int *pp = par_s + c * 9;
+            if (c == nC) {
+                pp[0] = 0; pp[1] = (doU && obj_v) ? nbps - 1 : 0; pp[2] = 0; pp[3] = 2 * segtot; pp[8] = 2 * segtot + 2;
+                pp[4] = S * GR * pitch; /* f_s follows D_s */
+                pp[5] = 1; pp[6] = 0; pp[7] = 0;
+            } else {
+                int sb = 0;
+                pp[0] = 0; pp[1] = 0; pp[2] = 0; pp[3] = 0; pp[4] = 0; pp[5] = 0; pp[6] = 0; pp[7] = 0; pp[8] = 0;
+                for (int j = 0; j < T.nout; j++) {
+                    const int clj = c - T.iC[j];
+                    if (clj >= 0 && clj < T.ncoef[j]) {
+                        const int ord = T.order[j];
+                        if (doU) {
+                            const int lo = __ldg(T.col_lo + c), hi = __ldg(T.col_hi + c);
+                            pp[0] = lo > 0 ? lo - 1 : 0;
+                            pp[1] = (hi < nbps - 2 ? hi : nbps - 2) + 1;
+                            pp[2] = __ldg(T.col_seg0 + c);
+                        }
+                        pp[3] = sb;
+                        pp[8] = segtot + sb;
+                        pp[4] = T.jk0[j] * GR * pitch;
+                        pp[5] = ord;
+                        pp[6] = clj;
+                        int iDI = 0, iDF = 0;
+                        if (doI && clj < ord) iDI = T.jk0[j] + clj + 1; /* offset 0, src/colloc.c:254 */
+                        if (doF) {
+                            const int k = clj - __ldg(T.seg_off[j] + T.nseg[j] - 1);
+                            if (k >= 0 && k < ord) iDF = T.jk0[j] + k + 1;
+                        }
+                        pp[7] = iDI | (iDF << 16);
                     }
-                    pp[3] = sb;
-                    pp[8] = segtot + sb;
-                    pp[4] = T.jk0[j] * GR * pitch;
-                    pp[5] = ord;
-                    pp[6] = clj;
-                    int iDI = 0, iDF = 0;
-                    if (doI && clj < ord) iDI = T.jk0[j] + clj + 1; /* offset 0, src/colloc.c:254 */
-                    if (doF) {
-                        const int k = clj - __ldg(T.seg_off[j] + T.nseg[j] - 1);
-                        if (k >= 0 && k < ord) iDF = T.jk0[j] + k + 1;
-                    }
-                    pp[7] = iDI | (iDF << 16);
+                    sb += T.nseg[j] + 1;
                 }
-                sb += T.nseg[j] + 1;
             }
         }
-        cols_s[c] = use_sched ? __ldg(sched_cols + c) : c;
     }
-    if (pdl) {
+    for (int c = tc; c <= nC; c += bdim) cols_s[c] = use_sched ? __ldg(sched_cols + c) : c;
+#ifdef NTG_BT_LATE
+    static_for<0, NOUT>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        constexpr int MD = PK::md(j);
+        constexpr int TB = pk_tab_base<PK>(j);
+        const int order = T.order[j];
+        offj[j] = active ? __ldg(T.off[j] + bp) : 0;
+#pragma unroll
+        for (int k = 0; k < PK::kMaxOrd; k++)
+#pragma unroll
+            for (int d = 0; d < MD; d++)
+                Bt[TB + k * MD + d] = (active && k < order) ? __ldg(T.Bt[j] + (size_t)(k * MD + d) * nbps + bp) : 0.0;
+    });
+#endif
+    if (flags & 1) {
         asm volatile("griddepcontrol.wait;" ::: "memory");
         if ((int)blockIdx.x < ntiles) stage_C(blockIdx.x, 0);
     }
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
-        const int p0 = tile * GR;
+        const int p0 = tile_p0(tile);
+        const int np = tile_np(tile, p0); /* problems of this tile */
         cp_async_wait_all();
         __syncthreads(); /* coefficients of this tile landed; phase B of the previous tile is done */
         if (tile + (int)gridDim.x < ntiles) stage_C(tile + gridDim.x, buf ^ 1);
         if constexpr (PUSH) { /* the previous tile's pairs (phase B of that tile ended at the barrier above) */
-            const int pq = p0 - (int)gridDim.x * GR + (int)threadIdx.x;
-            if ((int)threadIdx.x < GR && tile != (int)blockIdx.x && pq < P) push_pairs(res_s, dst_s, ndst, pq);
+            if (tile != (int)blockIdx.x) {
+                const int tp = tile - (int)gridDim.x, q0 = tile_p0(tp);
+                if ((int)threadIdx.x < tile_np(tp, q0)) push_pairs(res_s, dst_s, ndst, q0 + (int)threadIdx.x);
+            }
         }
 
         /* ---------------- phase A: this thread's breakpoint, R problems ---------------- */
@@ -531,7 +595,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
             for (int r = 0; r < R; r++) {
                 const int plr = r * G + pl;
                 const int p = p0 + plr;
-                if (p >= P) break;
+                if (plr >= np) break;
                 const double *Cp = C_s + (size_t)buf * tileC + (size_t)plr * nC;
                 double z[NZ > 0 ? NZ : 1];
                 double *zp[NOUT];
@@ -717,9 +781,8 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
         /* ------- phase B: one trapezoid chain per (problem, column); the scalar cost is column nC.
          * Thread = (slot, problem lane); a slot walks the columns the schedule gave it, so that all
          * slots carry the same number of terms and a warp's lanes run the same columns. ------- */
-        for (int plr = laneB; plr < GR; plr += lanesB) {
+        for (int plr = laneB; plr < np; plr += lanesB) {
             const int pb = p0 + plr;
-            if (pb >= P) break;
             for (int idx = it0; idx < it1; idx += istep) {
                 const int c = use_sched ? cols_s[idx] : idx;
                 if (c < nC && !want_g) continue;
@@ -801,7 +864,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
              * below covers any size) */
             const int chain_threads = (nC + 1) * GR;
             const int LV = (chain_threads + GR * 8 <= (int)blockDim.x) ? 8 : 4;
-            const int nv = GR * LV;
+            const int nv = np * LV;
             const int tv = (int)blockDim.x - 1 - (int)threadIdx.x;
             for (int base = 0; base < nv; base += blockDim.x) {
                 const int q = base + tv;
@@ -820,7 +883,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                 vm = fmax(vm, __shfl_xor_sync(0xffffffffu, vm, 1));
                 vm = fmax(vm, __shfl_xor_sync(0xffffffffu, vm, 2));
                 if (LV == 8) vm = fmax(vm, __shfl_xor_sync(0xffffffffu, vm, 4));
-                if (q < nv && part == 0 && p0 + plr < P) {
+                if (q < nv && part == 0 && plr < np) {
                     if constexpr (PUSH) res_s[2 * plr + 1] = vm;
                     else if constexpr (!PEERS) A.result[2 * (size_t)(p0 + plr) + 1] = vm;
                     else put_result(A, (size_t)(p0 + plr), 1, vm);
@@ -833,8 +896,9 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
     if constexpr (PUSH) { /* the last tile's pairs */
         const int nmine = ntiles > (int)blockIdx.x ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
         __syncthreads();
-        const int pq = ((int)blockIdx.x + (nmine - 1) * (int)gridDim.x) * GR + (int)threadIdx.x;
-        if (nmine > 0 && (int)threadIdx.x < GR && pq < P) push_pairs(res_s, dst_s, ndst, pq);
+        const int tl = (int)blockIdx.x + (nmine - 1) * (int)gridDim.x;
+        const int pl0 = nmine > 0 ? tile_p0(tl) : 0;
+        if (nmine > 0 && (int)threadIdx.x < tile_np(tl, pl0)) push_pairs(res_s, dst_s, ndst, pl0 + (int)threadIdx.x);
     }
 }
 
@@ -870,16 +934,53 @@ int launch_eval_small(const ntgb_launch *L)
      * batches, enough problems per tile that the whole batch is ONE wave of resident CTAs (a
      * second, mostly empty wave would double the latency); within ~100 KB of shared memory. */
     const int slots = (wide ? 1 : 2) * L->sm_count; /* __launch_bounds__(256, 2) / (512, 1) */
-    int R = (block + G * (T.nC + 1) - 1) / (G * (T.nC + 1));
+    const int ncol = T.nC + 1;
+    auto smem_rows = [&](int rows) { return SmallSmem{rows, nbps, T.S, T.nout, T.nC, segtot}.bytes(); };
+    int R = (block + G * ncol - 1) / (G * ncol);
     const int r_wave = (int)(((long long)P + (long long)G * slots - 1) / ((long long)G * slots));
     if (r_wave <= 8) R = r_wave;   /* single wave */
-    if (const char *er = getenv("NTG_B200_ROUNDS")) R = atoi(er); /* tuning experiments */
+    const char *er = getenv("NTG_B200_ROUNDS"); /* tuning experiments */
+    if (er) R = atoi(er);
     if (R < 1) R = 1;
     if (R > 8) R = 8;
     const size_t smem_cap = (size_t)(getenv("NTG_B200_SMEMCAP") ? atoi(getenv("NTG_B200_SMEMCAP")) : (wide ? 200 : 100)) * 1024;
-    while (R > 1 && SmallSmem{G * R, nbps, T.S, T.nout, T.nC, segtot}.bytes() > smem_cap) R--;
-    SmallSmem lay{G * R, nbps, T.S, T.nout, T.nC, segtot};
-    const size_t smem = lay.bytes();
+    while (R > 1 && smem_rows(G * R) > smem_cap) R--;
+    int rows = G * R; /* problems a tile's buffers hold */
+    /* Batches of a few tiles per CTA: whole tiles of G*R problems dealt round-robin leave some CTAs a
+     * tile more than others (8192 lane changes: 683 tiles of 12 on 296 CTAs, three for some and two
+     * for the rest; CFG-3: 228 tiles of 36 and 68 empty slots).  An EVEN split gives every CTA the same
+     * number of tiles, ktiles, and every tile P / (ktiles * grid) problems (+1 for the first few),
+     * with buffers of exactly that many rows.  Taken when it shortens the busiest CTA's critical path,
+     * counted as rounds of phase A plus passes of phase B over its (problem, column) chains. */
+    static const bool no_even = getenv("NTG_B200_NO_EVEN_SPLIT") != nullptr; /* A/B */
+    const int R_tiles = R, rows_tiles = rows;
+    int ktiles = 0, even_grid = 0;
+    if (!no_even && !er && P >= G) {
+        const long long nt = ((long long)P + rows - 1) / rows;
+        const long long grid_t = nt < slots ? nt : slots;
+        const long long per_cta_t = (nt + grid_t - 1) / grid_t;
+        if (per_cta_t <= 4) {
+            const long long cand = ((long long)P + G - 1) / G;
+            const int ge = cand < slots ? (int)cand : slots;
+            const int n = (P + ge - 1) / ge; /* problems of the busiest CTA */
+            int tcap = 8 * G < block ? 8 * G : block;
+            while (tcap > 1 && smem_rows(tcap) > smem_cap) tcap--;
+            const int k = (n + tcap - 1) / tcap;
+            if (k <= 15) {
+                const long long nte = (long long)k * ge;
+                const int tmax = (int)((P + nte - 1) / nte);
+                const int Re = (tmax + G - 1) / G;
+                auto cost = [&](int t, int r) { return r + (t * ncol + block - 1) / block; };
+                if ((long long)k * cost(tmax, Re) < per_cta_t * cost(rows, R)) {
+                    ktiles = k;
+                    even_grid = ge;
+                    R = Re;
+                    rows = tmax;
+                }
+            }
+        }
+    }
+    size_t smem = smem_rows(rows);
     if (smem > (size_t)L->max_smem_optin) return -1001;
     const ntgb_eval_args &a = L->args;
     const bool hot = a.mode_obj == 2 && a.mode_con == 2 && a.jac_layout == NTGB_JAC_BAND && a.J != nullptr &&
@@ -888,17 +989,30 @@ int launch_eval_small(const ntgb_launch *L)
     /* the steady-state kernel exists with and without the peer stores of the fused multi-GPU
      * gather, so that the single-GPU instantiation carries none of their code */
     static const bool force_peers = getenv("NTG_B200_FORCE_PEERS_KERNEL") != nullptr; /* A/B: code shape vs NVLink */
-    const bool push_ok = G * R <= block; /* one thread per pair of a tile */
-    auto kern = wide ? (full ? ntg_eval_small_kernel<PK, true, false, true, 512> : ntg_eval_small_kernel<PK, false, false, true, 512>)
-              : full ? (hot && (a.npeers == 0 || push_ok) ? ((a.npeers > 0 || force_peers) && push_ok ? ntg_eval_small_kernel<PK, true, true, true>
-                                             : ntg_eval_small_kernel<PK, true, true, false>)
-                            : ntg_eval_small_kernel<PK, true, false, true>)
-                     : ntg_eval_small_kernel<PK, false, false, true>;
+    using kern_t = void (*)(const ntgb_devtab, const ntgb_eval_args, int, int, int, int);
+    auto pick = [&](int tile_rows) -> kern_t {
+        const bool push_ok = tile_rows <= block; /* one thread per pair of a tile */
+        if (wide) return full ? ntg_eval_small_kernel<PK, true, false, true, 512> : ntg_eval_small_kernel<PK, false, false, true, 512>;
+        if (!full) return ntg_eval_small_kernel<PK, false, false, true>;
+        if (!(hot && (a.npeers == 0 || push_ok))) return ntg_eval_small_kernel<PK, true, false, true>;
+        return (a.npeers > 0 || force_peers) && push_ok ? ntg_eval_small_kernel<PK, true, true, true>
+                                                        : ntg_eval_small_kernel<PK, true, true, false>;
+    };
+    kern_t kern = pick(rows);
     int nb = 0;
     if (int rc = resident_blocks((const void *)kern, block, smem, L->max_smem_optin, &nb)) return rc;
-    const int ntiles = (P + G * R - 1) / (G * R);
+    if (ktiles > 0 && nb * L->sm_count < even_grid) { /* fewer resident CTAs than assumed: tiles of G*R */
+        ktiles = 0;
+        R = R_tiles;
+        rows = rows_tiles;
+        smem = smem_rows(rows);
+        kern = pick(rows);
+        if (int rc = resident_blocks((const void *)kern, block, smem, L->max_smem_optin, &nb)) return rc;
+    }
+    const int ntiles = (P + rows - 1) / rows;
     int grid = nb * L->sm_count;
     if (grid > ntiles) grid = ntiles;
+    if (ktiles > 0) grid = even_grid;
     if (grid < 1) return 0;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
@@ -916,10 +1030,12 @@ int launch_eval_small(const ntgb_launch *L)
         cfg.attrs = attr;
         cfg.numAttrs = 1;
     }
-    const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, T, L->args, G, R, segtot, pdl);
-    if (le != cudaSuccess && getenv("NTG_B200_DEBUG"))
-        fprintf(stderr, "K1s launch failed: grid %d block %d smem %zu G %d R %d P %d nb %d: %s\n", grid, block, smem, G,
-                R, P, nb, cudaGetErrorString(le));
+    static const bool no_rot = getenv("NTG_B200_NO_PUSH_ROTATE") != nullptr; /* A/B */
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, T, L->args, G, R, segtot, pdl | (no_rot ? 0 : 2) | (ktiles << 4) | (ktiles > 0 ? rows << 8 : 0));
+    static const bool dbg = getenv("NTG_B200_DEBUG") != nullptr;
+    if (dbg)
+        fprintf(stderr, "K1s launch: grid %d block %d smem %zu G %d R %d rows %d tiles/CTA (even split) %d P %d nb %d: %s\n",
+                grid, block, smem, G, R, rows, ktiles, P, nb, cudaGetErrorString(le));
     return (int)le;
 }
 

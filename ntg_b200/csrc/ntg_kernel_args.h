@@ -12,7 +12,7 @@
 
 #include <vector_types.h>
 
-#define NTGB_KERNEL_ABI 11
+#define NTGB_KERNEL_ABI 12
 #define NTGB_MAXOUT 8      /* outputs per problem the device tables can describe */
 #define NTGB_MAXORDER 20   /* PGS bsplvb work arrays: jmax = 20   */
 #define NTGB_MAXNLB 16     /* nonlinear bounds carried by value in the kernel params */
@@ -57,11 +57,10 @@ typedef struct ntgb_devtab {
     double nl_lb_v[NTGB_MAXNLB], nl_ub_v[NTGB_MAXNLB];
     /* quadrature schedule of the register-table kernel (K1s): the nC+1 trapezoid chains of a
      * problem (column nC = the scalar cost) packed into NS slots of near-equal length, longest
-     * chain first, for a CTA of NTGB_SCHED_BLOCK threads working on sched_G*(r+1) problems per
-     * tile, r = 0..7.  Table r starts at sched + r*(NTGB_SCHED_BLOCK+1 + nC+1): slot starts
-     * [NTGB_SCHED_BLOCK+1] (into the column list), then the column list [nC+1]. */
-    int sched_G;
-    int sched_ns[8];
+     * chain first, for NS = 1 .. sched_maxns.  Table NS starts at
+     * sched + (NS-1)*(NTGB_SCHED_BLOCK+1 + nC+1): slot starts [NTGB_SCHED_BLOCK+1] (into the column
+     * list), then the column list [nC+1]. */
+    int sched_maxns;
     /* steady-state cluster kernel (K1c/H): a second plan follows the first in the same arrays --
      * plan_ptr[ncoef+1 .. 2*ncoef+2) and plan[plan_n ..) -- in which every column belongs to ONE
      * CTA (columns are dealt in contiguous ranges, rank r owns [ncoef*r/CL, ncoef*(r+1)/CL)) and
@@ -72,9 +71,17 @@ typedef struct ntgb_devtab {
     int plan_halo;
     int plan_share;                 /* second plan: most entries any one rank owns */
     const int *sched;
+    /* K1s steady state (funobj mode 2 + funcon mode 2): the tile-invariant shared-memory tables of
+     * the kernel, laid out once.  img_w = [2][pitch+2] quadrature weights (dt, then node weights);
+     * img_i = run starts [segtot], run offsets [segtot], the cost's run {0, nbps, 0, 0}, then 9 ints
+     * per column 0..nC (the chain descriptions of ntg_eval_small.cuh, entry [4] WITHOUT its factor
+     * G*R, the problems per tile, which only the launch knows) */
+    const double *img_w;
+    const int *img_i;
 } ntgb_devtab;
 
 #define NTGB_SCHED_BLOCK 256
+#define NTGB_SCHED_MAXNS 32
 
 /* cluster geometry of K1c for a horizon of nbps breakpoints: at most `per_cta` (<= 224) breakpoints per
  * CTA -- 7 warps pinned to breakpoints + 1 service warp = 256 threads.  Decided once at create time

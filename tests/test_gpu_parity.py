@@ -286,6 +286,30 @@ def test_batch_independence_and_full_size_properties(torch_cuda):
     pb.close()
 
 
+@pytest.mark.parametrize("cfg,P", [("cfg3", 8192), ("cfg3", 3553), ("cfg4", 4096), ("cfg4", 8192), ("cfg4", 8189), ("cfg4", 4737),
+                                   ("cfg2", 7105)])
+@pytest.mark.parametrize("fast", [False, True], ids=["exact", "fast"])
+def test_even_split_launch_geometries(torch_cuda, cfg, P, fast):
+    """Batches of a few tiles per CTA are split EVENLY over the CTAs (ntg_eval_small.cuh::
+    launch_eval_small: one or two tiles per CTA of P / (k * grid) problems, +1 for the first few):
+    every output, including the (objective, violation) table, is bit-identical to the same problems
+    evaluated in slices that take the other geometry (whole tiles of G*R problems)."""
+    torch = torch_cuda
+    from ntg_b200 import Problem
+    spec, _ = configs.get(cfg)
+    X = torch.from_numpy(configs.coefficients(cfg, P, spec, seed=P)).cuda()
+    pb = Problem(spec, 0, fast=fast)
+    a = pb.eval(X)
+    torch.cuda.synchronize()
+    step = 1000 if cfg != "cfg4" else 777   # one wave of whole tiles
+    for lo in range(0, P, step):
+        hi = min(P, lo + step)
+        d = pb.eval(X[lo:hi].contiguous())
+        for k in ("f", "g", "c", "J", "result"):
+            assert torch.equal(d[k], a[k][lo:hi]), f"{cfg} P={P} [{lo},{hi}): {k} depends on the launch geometry"
+    pb.close()
+
+
 def test_eval_host_path_matches_device_path(torch_cuda, port):
     """ntgb_eval_host (host buffers, H2D/D2H inside) == ntgb_eval on device buffers"""
     from ntg_b200 import Problem

@@ -18,12 +18,13 @@ def rep(old, new):
     assert old in s, old
     s = s.replace(old, new, 1)
 
-rep('namespace ntgb {\n', 'namespace ntgb {\n__device__ unsigned long long g_stamps[8 * 16];\n'
+rep('namespace ntgb {\n', 'namespace ntgb {\n__device__ unsigned long long g_stamps[8 * 3 * 8];\n'
     '__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }\n'
-    '#define STAMP(i) do { if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) g_stamps[(blockIdx.x == 0 ? 0 : 16) + (i)] = gtime(); } while (0)\n')
-rep('    int buf = 0;\n    /* pdl: launched', '    STAMP(0);\n    int buf = 0;\n    /* pdl: launched')
-rep('    if (pdl) {\n        asm volatile("griddepcontrol.wait;" ::: "memory");',
-    '    __syncthreads(); STAMP(1);\n    if (pdl) {\n        asm volatile("griddepcontrol.wait;" ::: "memory");\n        STAMP(2);')
+    '#define STAMP(i) do { if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1 || blockIdx.x == gridDim.x / 2)) g_stamps[(A.nstate & 7) * 24 + (blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x - 1 ? 16 : 8)) + (i)] = gtime(); } while (0)\n')
+rep('    extern __shared__ double smem[];\n', '    extern __shared__ double smem[];\n    STAMP(0);\n')
+rep('    for (int q = threadIdx.x; q < GR; q += blockDim.x) {\n        cI_s[q] = 0.0;', '    STAMP(7);\n    for (int q = threadIdx.x; q < GR; q += blockDim.x) {\n        cI_s[q] = 0.0;')
+rep('    if (pdl & 1) {\n        asm volatile("griddepcontrol.wait;" ::: "memory");',
+    '    __syncthreads(); STAMP(1);\n    if (pdl & 1) {\n        asm volatile("griddepcontrol.wait;" ::: "memory");\n        STAMP(2);')
 rep('        cp_async_wait_all();\n        __syncthreads(); /* coefficients of this tile landed',
     '        cp_async_wait_all();\n        __syncthreads(); STAMP(3); /* coefficients of this tile landed')
 rep('        __syncthreads();\n\n        /* ------- phase B:', '        __syncthreads(); STAMP(4);\n\n        /* ------- phase B:')
@@ -31,18 +32,19 @@ rep('        /* the barrier at the top of the next iteration separates this phas
     '        __syncthreads(); STAMP(5);\n    }')
 rep('    cp_async_wait_all();\n    if constexpr (PUSH) { /* the last tile', '    STAMP(6);\n    cp_async_wait_all();\n    if constexpr (PUSH) { /* the last tile')
 open(p, "w").write(s)
-out = os.path.join(ROOT, "build", "variants", "stamps")
-os.makedirs(out, exist_ok=True)
-for name in ("vdp_fast", "kincar_fast"):
-    m = [x for x in build.repo_packs() if x.name == name][0]
-    w = build.generate_wrapper(m)
-    txt = open(w).read() + ('\nextern "C" void ntg_read_stamps(unsigned long long *o) '
-                            '{ cudaMemcpyFromSymbol(o, ntgb::g_stamps, sizeof(unsigned long long) * 128); }\n')
-    w2 = os.path.join(scr, f"pack_{name}.cu")
-    open(w2, "w").write(txt)
-    common = list(build.COMMON)
-    common[common.index(build.CSRC)] = os.path.join(scr, "csrc")
-    cmd = [build.nvcc()] + build.ARCH + common + ["-fmad=true", "-o", os.path.join(out, f"libntgpack_{name}.so"), w2,
-                                                  "-L", build.LIB, "-lntg_b200", "-Xlinker", "-rpath=" + build.LIB, "-Xlinker", "-Bsymbolic"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    print(name, "rc", r.returncode, r.stderr[-400:])
+for vdir, extra in (("stamps", []), ("stamps_late", ["-DNTG_BT_LATE"])):
+    out = os.path.join(ROOT, "build", "variants", vdir)
+    os.makedirs(out, exist_ok=True)
+    for name in ("vdp_fast", "kincar_fast"):
+        m = [x for x in build.repo_packs() if x.name == name][0]
+        w = build.generate_wrapper(m)
+        txt = open(w).read() + ('\nextern "C" void ntg_read_stamps(unsigned long long *o) '
+                                '{ cudaMemcpyFromSymbol(o, ntgb::g_stamps, sizeof(unsigned long long) * 192); }\n')
+        w2 = os.path.join(scr, f"pack_{name}.cu")
+        open(w2, "w").write(txt)
+        common = list(build.COMMON)
+        common[common.index(build.CSRC)] = os.path.join(scr, "csrc")
+        cmd = [build.nvcc()] + build.ARCH + common + extra + ["-fmad=true", "-o", os.path.join(out, f"libntgpack_{name}.so"), w2,
+                                                      "-L", build.LIB, "-lntg_b200", "-Xlinker", "-rpath=" + build.LIB, "-Xlinker", "-Bsymbolic"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        print(vdir, name, "rc", r.returncode, r.stderr[-400:])

@@ -328,10 +328,10 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
     constexpr int NZ = pk_nz<PK>();
     constexpr int NB = pk_tab_doubles<PK>();
     extern __shared__ double smem[];
-    /* flags: bit 0 programmatic dependent launch, bit 1 rotate the peer-store order, bits 4-7 tiles per
-     * CTA of an EVEN split (0: tiles of G*R problems dealt round-robin), bits 8.. rows of a tile's
+    /* flags: bit 0 programmatic dependent launch, bit 1 rotate the peer-store order, bits 4-9 tiles per
+     * CTA of an EVEN split (0: tiles of G*R problems dealt round-robin), bits 10.. rows of a tile's
      * buffers in an even split (>= the largest tile; G*R otherwise) */
-    const int GR = (flags >> 8) ? (flags >> 8) : G * R;
+    const int GR = (flags >> 10) ? (flags >> 10) : G * R;
     const SmallSmem L{GR, T.nbps, T.S, T.nout, T.nC, segtot};
     const int nbps = T.nbps, pitch = L.pitch(), nC = T.nC, P = A.P, S = T.S;
     double *D_s = smem + L.D_off();
@@ -393,7 +393,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
      * split evenly over the tiles (tq or tq + 1 each).  Whole tiles of GR leave a third of the CTA
      * slots empty at CFG-3 and put three full rounds on the others; 8192 lane changes are 683 tiles
      * of 12, three for some CTAs and two for the rest */
-    const int ktiles = (flags >> 4) & 15;
+    const int ktiles = (flags >> 4) & 63;
     const bool even = ktiles != 0;
     const int ntiles = even ? ktiles * (int)gridDim.x : (P + GR - 1) / GR;
     const int tq = even ? P / ntiles : GR, trem = even ? P - tq * ntiles : 0;
@@ -951,7 +951,9 @@ int launch_eval_small(const ntgb_launch *L)
      * for the rest; CFG-3: 228 tiles of 36 and 68 empty slots).  An EVEN split gives every CTA the same
      * number of tiles, ktiles, and every tile P / (ktiles * grid) problems (+1 for the first few),
      * with buffers of exactly that many rows.  Taken when it shortens the busiest CTA's critical path,
-     * counted as rounds of phase A plus passes of phase B over its (problem, column) chains. */
+     * counted as rounds of phase A plus passes of phase B over its (problem, column) chains (measured,
+     * lane changes of 64 breakpoints: 4096 problems 12.6 -> 10.9 us, 8192 21.4 -> 18.8, 16384 36.2 -> 34.3,
+     * 32768 65.2 -> 64.5; no difference beyond). */
     static const bool no_even = getenv("NTG_B200_NO_EVEN_SPLIT") != nullptr; /* A/B */
     const int R_tiles = R, rows_tiles = rows;
     int ktiles = 0, even_grid = 0;
@@ -959,19 +961,22 @@ int launch_eval_small(const ntgb_launch *L)
         const long long nt = ((long long)P + rows - 1) / rows;
         const long long grid_t = nt < slots ? nt : slots;
         const long long per_cta_t = (nt + grid_t - 1) / grid_t;
-        if (per_cta_t <= 4) {
+        static const int even_max = getenv("NTG_B200_EVEN_MAXTILES") ? atoi(getenv("NTG_B200_EVEN_MAXTILES")) : 8; /* tuning */
+        if (per_cta_t <= even_max) {
             const long long cand = ((long long)P + G - 1) / G;
             const int ge = cand < slots ? (int)cand : slots;
             const int n = (P + ge - 1) / ge; /* problems of the busiest CTA */
             int tcap = 8 * G < block ? 8 * G : block;
             while (tcap > 1 && smem_rows(tcap) > smem_cap) tcap--;
             const int k = (n + tcap - 1) / tcap;
-            if (k <= 15) {
+            if (k <= 63) {
                 const long long nte = (long long)k * ge;
                 const int tmax = (int)((P + nte - 1) / nte);
                 const int Re = (tmax + G - 1) / G;
                 auto cost = [&](int t, int r) { return r + (t * ncol + block - 1) / block; };
-                if ((long long)k * cost(tmax, Re) < per_cta_t * cost(rows, R)) {
+                /* a tie goes to the even split when some CTAs would get a tile more than others, and to whole
+                 * tiles for one tile per CTA (fewer CTAs: more of the next launch's prologues overlap) */
+                if ((long long)k * cost(tmax, Re) < per_cta_t * cost(rows, R) + (per_cta_t > 1 ? 1 : 0)) {
                     ktiles = k;
                     even_grid = ge;
                     R = Re;
@@ -1031,7 +1036,7 @@ int launch_eval_small(const ntgb_launch *L)
         cfg.numAttrs = 1;
     }
     static const bool no_rot = getenv("NTG_B200_NO_PUSH_ROTATE") != nullptr; /* A/B */
-    const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, T, L->args, G, R, segtot, pdl | (no_rot ? 0 : 2) | (ktiles << 4) | (ktiles > 0 ? rows << 8 : 0));
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, T, L->args, G, R, segtot, pdl | (no_rot ? 0 : 2) | (ktiles << 4) | (ktiles > 0 ? rows << 10 : 0));
     static const bool dbg = getenv("NTG_B200_DEBUG") != nullptr;
     if (dbg)
         fprintf(stderr, "K1s launch: grid %d block %d smem %zu G %d R %d rows %d tiles/CTA (even split) %d P %d nb %d: %s\n",

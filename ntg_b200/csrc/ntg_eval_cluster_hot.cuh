@@ -573,7 +573,7 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int cwi
                         st_stream(A.c + (size_t)p * T.ncnln + m, cv[m]);
                         viol = fmax(viol, row_violation(cv[m], nl_bound(T, false, m), nl_bound(T, true, m)));
                     }
-                    emit_rows_regs<PK, true, PK::kNnlic, 0, true, true>(T, A, Bt, offj, p, bp, dfc, 0);
+                    emit_rows_regs<PK, true, PK::kNnlic, 0, true, 1>(T, A, Bt, offj, p, bp, dfc, 0);
                 }
             }
             /* nonlinear final constraints (last breakpoint), src/constraints.c:165-195 */
@@ -602,7 +602,7 @@ ntg_eval_cluster_hot_kernel(const ntgb_devtab T, const ntgb_eval_args A, int cwi
                         viol = fmax(viol, row_violation(cv[m], nl_bound(T, false, T.nnlic + T.nnltc + m),
                                                         nl_bound(T, true, T.nnlic + T.nnltc + m)));
                     }
-                    emit_rows_regs<PK, true, PK::kNnlfc, 2, true, true>(T, A, Bt, offj, p, bp, dfc, rb);
+                    emit_rows_regs<PK, true, PK::kNnlfc, 2, true, 1>(T, A, Bt, offj, p, bp, dfc, rb);
                 }
             }
             if (viol > 0.0) atomicMax(viol_s + buf, (unsigned long long)__double_as_longlong(viol));

@@ -262,21 +262,32 @@ __device__ __forceinline__ void emit_rows_layout(const ntgb_devtab &T, const ntg
             }
         });
     } else {
-        double *Jp = A.J + (size_t)p * T.ncnln * T.nC;
+        /* NPSOL's dense column-major J[col * ncnln + row] (src/ntg.c:217-220): consecutive breakpoints
+         * are consecutive rows of one column inside a knot interval, so a warp's stores coalesce.  One
+         * base per output (its first column at this breakpoint, this thread's row); a band entry
+         * (m, j, k) is then k columns and m row blocks away: one multiply-add per address. */
+        const unsigned ld = (unsigned)T.ncnln;
+        double *Jj[PK::kNout];
+        static_for<0, PK::kNout>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            Jj[j] = A.J + ((size_t)p * T.nC + (unsigned)(T.iC[j] + (KIND == 0 ? 0 : offj[j]))) * ld +
+                    (unsigned)(KIND == 1 ? row_base + bp : row_base);
+        });
+        const unsigned rstep = KIND == 1 ? (unsigned)nbps : 1u;
         static_for<0, NCON>([&](auto mc) {
             constexpr int m = decltype(mc)::value;
             constexpr unsigned long long MASK = SPARSE ? sp_con<PK, KIND>(MOFF + m) : kDense;
-            const int row = (KIND == 1) ? row_base + m * nbps + bp : row_base + m;
             band_from_regs<PK, FULL, ONE, MASK>(T, Bt, dfc[m], [&](auto jc, auto kc, double v) {
                 constexpr int j = decltype(jc)::value;
-                const int col = T.iC[j] + (KIND == 0 ? 0 : offj[j]) + decltype(kc)::value;
-                st_stream(Jp + (size_t)col * T.ncnln + row, v);
+                constexpr unsigned k = (unsigned)decltype(kc)::value;
+                st_stream(Jj[j] + (k * ld + (unsigned)m * rstep), v);
             });
         });
     }
 }
 
-template <class PK, bool FULL, int NCON, int KIND, bool ONE = false, bool HOT = false>
+/* JL: the Jacobian layout when the kernel knows it at compile time (1 band, 2 dense), else 0 */
+template <class PK, bool FULL, int NCON, int KIND, bool ONE = false, int JL = 0>
 __device__ __forceinline__ void emit_rows_regs(const ntgb_devtab &T, const ntgb_eval_args &A, const double *Bt,
                                                const int *offj, int p, int bp, const double (&dfc)[NCON][pk_nz<PK>()],
                                                int row_base)
@@ -286,7 +297,7 @@ __device__ __forceinline__ void emit_rows_regs(const ntgb_devtab &T, const ntgb_
         constexpr int m = decltype(mc)::value;
         clean = clean && sp_clean<pk_nz<PK>()>(dfc[m], sp_con<PK, KIND>(m));
     });
-    const bool band = HOT || A.jac_layout == NTGB_JAC_BAND;
+    const bool band = JL == 1 || (JL == 0 && A.jac_layout == NTGB_JAC_BAND);
     if (band) {
         if (clean) emit_rows_layout<PK, FULL, NCON, KIND, ONE, true, true>(T, A, Bt, offj, p, bp, dfc, row_base);
         else emit_rows_layout<PK, FULL, NCON, KIND, ONE, true, false>(T, A, Bt, offj, p, bp, dfc, row_base);
@@ -319,8 +330,9 @@ __device__ __noinline__ void push_pairs(const double *res_s, double2 *const *dst
 }
 
 /* HOT = the solver's steady state, known at compile time: funobj mode 2 + funcon mode 2, Jacobian
+ * in band layout -- or, DENSE, in NPSOL's dense column-major layout (what ntg()'s funcon hands NPSOL) --
  * in band layout, f / g / c / J all requested, Z not requested. */
-template <class PK, bool FULL, bool HOT = false, bool PEERS = true, int BLOCK = 256>
+template <class PK, bool FULL, bool HOT = false, bool PEERS = true, int BLOCK = 256, bool DENSE = false>
 __global__ void __launch_bounds__(BLOCK, 512 / BLOCK)
 ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R, int segtot, int flags)
 {
@@ -657,7 +669,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                                                                 nl_bound(T, true, T.nnlic + m)));
                             }
                         }
-                        if (wantJ) emit_rows_regs<PK, FULL, PK::kNnltc, 1, false, HOT>(T, A, Bt, offj, p, bp, dfc, T.nnlic);
+                        if (wantJ) emit_rows_regs<PK, FULL, PK::kNnltc, 1, false, (HOT ? (DENSE ? 2 : 1) : 0)>(T, A, Bt, offj, p, bp, dfc, T.nnlic);
                     }
                 }
                 /* nonlinear initial constraints (breakpoint 0), src/constraints.c:88-117 */
@@ -683,7 +695,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                                 viol = fmax(viol, row_violation(cv[m], nl_bound(T, false, m), nl_bound(T, true, m)));
                             }
                         }
-                        if (wantJ) emit_rows_regs<PK, FULL, PK::kNnlic, 0, false, HOT>(T, A, Bt, offj, p, bp, dfc, 0);
+                        if (wantJ) emit_rows_regs<PK, FULL, PK::kNnlic, 0, false, (HOT ? (DENSE ? 2 : 1) : 0)>(T, A, Bt, offj, p, bp, dfc, 0);
                     }
                 }
                 /* nonlinear final constraints (last breakpoint), src/constraints.c:165-195 */
@@ -711,7 +723,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
                                                                 nl_bound(T, true, T.nnlic + T.nnltc + m)));
                             }
                         }
-                        if (wantJ) emit_rows_regs<PK, FULL, PK::kNnlfc, 2, false, HOT>(T, A, Bt, offj, p, bp, dfc, rb);
+                        if (wantJ) emit_rows_regs<PK, FULL, PK::kNnlfc, 2, false, (HOT ? (DENSE ? 2 : 1) : 0)>(T, A, Bt, offj, p, bp, dfc, rb);
                     }
                 }
                 /* per-breakpoint violation; phase B takes the maximum over the breakpoints (a maximum
@@ -988,9 +1000,12 @@ int launch_eval_small(const ntgb_launch *L)
     size_t smem = smem_rows(rows);
     if (smem > (size_t)L->max_smem_optin) return -1001;
     const ntgb_eval_args &a = L->args;
-    const bool hot = a.mode_obj == 2 && a.mode_con == 2 && a.jac_layout == NTGB_JAC_BAND && a.J != nullptr &&
-                     a.f != nullptr && a.g != nullptr && a.c != nullptr && a.Z == nullptr && T.ncnln > 0 &&
+    const bool steady = a.mode_obj == 2 && a.mode_con == 2 && a.J != nullptr && a.f != nullptr && a.g != nullptr &&
+                        a.c != nullptr && a.Z == nullptr && T.ncnln > 0;
+    const bool hot = steady && a.jac_layout == NTGB_JAC_BAND &&
                      ((uintptr_t)a.result & 15u) == 0; /* the peer-store variant writes (objective, violation) as one 16-byte pair */
+    /* the same steady state with NPSOL's dense column-major Jacobian (single GPU) */
+    const bool hot_dense = steady && a.jac_layout == NTGB_JAC_DENSE && a.npeers == 0;
     /* the steady-state kernel exists with and without the peer stores of the fused multi-GPU
      * gather, so that the single-GPU instantiation carries none of their code */
     static const bool force_peers = getenv("NTG_B200_FORCE_PEERS_KERNEL") != nullptr; /* A/B: code shape vs NVLink */
@@ -999,6 +1014,7 @@ int launch_eval_small(const ntgb_launch *L)
         const bool push_ok = tile_rows <= block; /* one thread per pair of a tile */
         if (wide) return full ? ntg_eval_small_kernel<PK, true, false, true, 512> : ntg_eval_small_kernel<PK, false, false, true, 512>;
         if (!full) return ntg_eval_small_kernel<PK, false, false, true>;
+        if (hot_dense) return ntg_eval_small_kernel<PK, true, true, false, 256, true>;
         if (!(hot && (a.npeers == 0 || push_ok))) return ntg_eval_small_kernel<PK, true, false, true>;
         return (a.npeers > 0 || force_peers) && push_ok ? ntg_eval_small_kernel<PK, true, true, true>
                                                         : ntg_eval_small_kernel<PK, true, true, false>;

@@ -375,7 +375,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
         if (t == 0 && loc) dst_s[0] = reinterpret_cast<double2 *>(A.result);
         /* every CTA starts its round over the ranks at a different one (flags bit 1): 8 ranks x 296 CTAs
          * that all store to rank 0 first, then rank 1, ... would take turns on one NVLink port at a time */
-        const int rot = (flags & 2) ? (int)(blockIdx.x % (unsigned)A.npeers) : 0;
+        const int rot = ((flags & 2) && A.npeers > 1) ? (int)(blockIdx.x % (unsigned)A.npeers) : 0;
         if (t < A.npeers) {
             const int src = t + rot < A.npeers ? t + rot : t + rot - A.npeers;
             dst_s[loc + t] = reinterpret_cast<double2 *>(A.peer_result[src]) + A.peer_row0;
@@ -401,27 +401,39 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
     /* the first tile's coefficients are requested before anything else: small batches are one tile
      * per CTA and this latency would otherwise sit behind the table loads below */
     /* tiles: GR problems each, dealt round-robin to the CTAs -- or, for a batch of a few tiles per CTA
-     * (launch_eval_small), an EVEN split: every CTA gets the same number of tiles and the problems are
-     * split evenly over the tiles (tq or tq + 1 each).  Whole tiles of GR leave a third of the CTA
-     * slots empty at CFG-3 and put three full rounds on the others; 8192 lane changes are 683 tiles
-     * of 12, three for some CTAs and two for the rest */
-    const int ktiles = (flags >> 4) & 63;
-    const bool even = ktiles != 0;
-    const int ntiles = even ? ktiles * (int)gridDim.x : (P + GR - 1) / GR;
-    const int tq = even ? P / ntiles : GR, trem = even ? P - tq * ntiles : 0;
-    auto tile_p0 = [&](int tile) { return tile * tq + (tile < trem ? tile : trem); };
-    auto tile_np = [&](int tile, int p0) {
-        const int n = tq + (tile < trem ? 1 : 0);
-        return p0 + n > P ? P - p0 : n;
-    };
+     * (launch_eval_small), an EVEN split: CTA b owns the contiguous problems [b*P/grid, (b+1)*P/grid)
+     * and walks them in tiles of GR (the launcher sizes GR so that every CTA needs the same number of
+     * tiles).  Whole tiles of GR dealt round-robin leave a third of the CTA slots empty at CFG-3 and
+     * put three full rounds on the others; 8192 lane changes are 683 tiles of 12, three for some CTAs
+     * and two for the rest.  Either way a CTA's tiles are p_first, p_first + pstride, ... below pend:
+     * the tile loop costs one add and one minimum per tile. */
+    const bool even = ((flags >> 4) & 63) != 0;
+    int p_first, pstride, pend;
+    if (even) {
+        const int q = P / (int)gridDim.x, rem = P - q * (int)gridDim.x, b = (int)blockIdx.x;
+        p_first = b * q + (b < rem ? b : rem);
+        pend = p_first + q + (b < rem ? 1 : 0);
+        pstride = GR;
+    } else {
+        p_first = (int)blockIdx.x * GR;
+        pend = P;
+        pstride = (int)gridDim.x * GR;
+    }
     const int tileC = GR * nC; /* doubles of coefficients a tile's buffer holds (contiguous in global memory) */
-    auto stage_C = [&](int tile, int buf) {
-        const int q0 = tile_p0(tile);
-        const int cnt = tile_np(tile, q0) * nC;
+    auto stage_C = [&](int q0, int nq, int buf) { /* problems [q0, q0 + nq) */
+        const int cnt = nq * nC;
         const double *src = A.C + (long long)q0 * nC;
         for (int e = threadIdx.x; e < cnt; e += blockDim.x) cp_async8(C_s + (size_t)buf * tileC + e, src + e);
         cp_async_commit();
     };
+    /* tiles of this CTA: p_first + it * pstride for it < ntl, GR problems each but possibly the last */
+    int ntl = pend > p_first ? (pend - p_first + pstride - 1) / pstride : 0;
+    /* (the same value in every lane; read back from lane 0, the loop bound sits in a register of its own.
+     * This kernel's run time moves by +-5 % with the instruction schedule ptxas picks for phase A, and that
+     * moves with the spelling of this loop: measured with tools/variants_perf.sh on the steady-state
+     * instantiations with and without the peer stores -- 125.1 / 122.3 us with this line, 130 / 123 with
+     * p0 and np carried across iterations, 124.5 / 130.5 with the tile index as the loop variable) */
+    ntl = __shfl_sync(0xffffffffu, ntl, 0);
     int buf = 0;
     /* flags bit 0: launched with programmatic stream serialization -- this grid may start while the grid in
      * front of it in the stream is still running.  Everything up to griddepcontrol.wait only reads
@@ -429,7 +441,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
      * previous launch; coefficients are read and results written after the wait.  The grid behind
      * this one may start its own prologue as soon as every CTA of this grid is resident. */
     if (flags & 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    else if ((int)blockIdx.x < ntiles) stage_C(blockIdx.x, 0);
+    else if (ntl > 0) stage_C(p_first, pend - p_first < GR ? pend - p_first : GR, 0);
 
     /* ---- once per CTA: dt, offset runs, accumulators; once per thread: its table slice ----
      * A thread's table slice is requested FIRST (it is only consumed in phase A), and the three
@@ -503,8 +515,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
 
     /* phase-B mapping (tile-invariant): slot and problem lane of this thread, its column list */
     const bool want_g = HOT || (obj_d && A.g != nullptr);
-    const int tmax = even ? tq + (trem ? 1 : 0) : GR; /* problems of the largest tile */
-    const int lanesB = tmax < (int)blockDim.x ? tmax : (int)blockDim.x;
+    const int lanesB = GR < (int)blockDim.x ? GR : (int)blockDim.x;
     const int slotB = threadIdx.x / lanesB, laneB = threadIdx.x - slotB * lanesB;
     const int NSB = (int)blockDim.x / lanesB;
     const bool use_sched = T.sched != nullptr && blockDim.x == NTGB_SCHED_BLOCK;
@@ -586,20 +597,18 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
 #endif
     if (flags & 1) {
         asm volatile("griddepcontrol.wait;" ::: "memory");
-        if ((int)blockIdx.x < ntiles) stage_C(blockIdx.x, 0);
+        if (ntl > 0) stage_C(p_first, pend - p_first < GR ? pend - p_first : GR, 0);
     }
 
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
-        const int p0 = tile_p0(tile);
-        const int np = tile_np(tile, p0); /* problems of this tile */
+    for (int it = 0; it < ntl; it++, buf ^= 1) {
+        const int p0 = p_first + it * pstride;
+        const int np = pend - p0 < GR ? pend - p0 : GR; /* problems of this tile */
         cp_async_wait_all();
         __syncthreads(); /* coefficients of this tile landed; phase B of the previous tile is done */
-        if (tile + (int)gridDim.x < ntiles) stage_C(tile + gridDim.x, buf ^ 1);
-        if constexpr (PUSH) { /* the previous tile's pairs (phase B of that tile ended at the barrier above) */
-            if (tile != (int)blockIdx.x) {
-                const int tp = tile - (int)gridDim.x, q0 = tile_p0(tp);
-                if ((int)threadIdx.x < tile_np(tp, q0)) push_pairs(res_s, dst_s, ndst, q0 + (int)threadIdx.x);
-            }
+        if (it + 1 < ntl) stage_C(p0 + pstride, pend - p0 - pstride < GR ? pend - p0 - pstride : GR, buf ^ 1);
+        if constexpr (PUSH) { /* the previous tile's pairs (phase B of that tile ended at the barrier above);
+                               * a tile that has a successor is a full one */
+            if (it > 0 && (int)threadIdx.x < GR) push_pairs(res_s, dst_s, ndst, p0 - pstride + (int)threadIdx.x);
         }
 
         /* ---------------- phase A: this thread's breakpoint, R problems ---------------- */
@@ -906,11 +915,10 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
     }
     cp_async_wait_all();
     if constexpr (PUSH) { /* the last tile's pairs */
-        const int nmine = ntiles > (int)blockIdx.x ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
         __syncthreads();
-        const int tl = (int)blockIdx.x + (nmine - 1) * (int)gridDim.x;
-        const int pl0 = nmine > 0 ? tile_p0(tl) : 0;
-        if (nmine > 0 && (int)threadIdx.x < tile_np(tl, pl0)) push_pairs(res_s, dst_s, ndst, pl0 + (int)threadIdx.x);
+        const int pl0 = p_first + (ntl - 1) * pstride;
+        const int npl = pend - pl0 < GR ? pend - pl0 : GR;
+        if (ntl > 0 && (int)threadIdx.x < npl) push_pairs(res_s, dst_s, ndst, pl0 + (int)threadIdx.x);
     }
 }
 

@@ -9,8 +9,8 @@ import numpy as np, torch
 from ntg_b200 import configs, Problem, JAC_BAND
 from ntg_b200 import problem as _p
 
-NAMES = ["start", "wt", "prol", "wait", "C", "A", "B", "end"]
-ORDER = [0, 7, 1, 2, 3, 4, 5, 6]
+NAMES = ["start", "prol", "wait", "C", "A", "chains", "B", "end"]
+ORDER = [0, 1, 2, 3, 4, 7, 5, 6]
 cases = [("cfg2", 0), ("cfg3", 0)]
 for cfg, Pover in cases:
     spec, P = configs.get(cfg)

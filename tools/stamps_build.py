@@ -22,7 +22,7 @@ rep('namespace ntgb {\n', 'namespace ntgb {\n__device__ unsigned long long g_sta
     '__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }\n'
     '#define STAMP(i) do { if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1 || blockIdx.x == gridDim.x / 2)) g_stamps[(A.nstate & 7) * 24 + (blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x - 1 ? 16 : 8)) + (i)] = gtime(); } while (0)\n')
 rep('    extern __shared__ double smem[];\n', '    extern __shared__ double smem[];\n    STAMP(0);\n')
-rep('    for (int q = threadIdx.x; q < GR; q += blockDim.x) {\n        cI_s[q] = 0.0;', '    STAMP(7);\n    for (int q = threadIdx.x; q < GR; q += blockDim.x) {\n        cI_s[q] = 0.0;')
+rep('        /* maximum constraint violation per problem: eight lanes per problem', '        STAMP(7);\n        /* maximum constraint violation per problem: eight lanes per problem')
 rep('    if (flags & 1) {\n        asm volatile("griddepcontrol.wait;" ::: "memory");',
     '    __syncthreads(); STAMP(1);\n    if (flags & 1) {\n        asm volatile("griddepcontrol.wait;" ::: "memory");\n        STAMP(2);')
 rep('        cp_async_wait_all();\n        __syncthreads(); /* coefficients of this tile landed',

@@ -1864,8 +1864,10 @@ int ntgb_eval_host(ntgb_problem *pb, const ntgb_eval_args *h)
     const size_t jper = h->jac_layout == NTGB_JAC_DENSE ? (size_t)d.ncnln * d.nC
                       : h->jac_layout == NTGB_JAC_BAND  ? (size_t)d.ncnln * d.sorder : 0;
     /* chunking: one chunk for small batches (an NPSOL callback is P = 1); otherwise chunks of
-     * >= 1024 problems and ~64 MB of results, alternating between the two buffer sets so copies
-     * overlap compute.  Host buffers should be page-locked (cudaHostRegister / cudaMallocHost)
+     * >= 1024 problems and ~192 MB of results (measured on CFG-4, 747 MB per call: 32 MB chunks 13.9 ms,
+     * 64 MB 13.5, 192 MB 13.3 = 0.98 of one plain pinned copy of the same bytes; every chunk costs five
+     * device-to-host copies, the small ones mostly latency), alternating between the two buffer sets so
+     * copies overlap compute.  Host buffers should be page-locked (cudaHostRegister / cudaMallocHost)
      * for the copies to be asynchronous; pageable memory works, without the overlap. */
     const size_t per = sizeof(double) * ((size_t)2 * d.nC + 3 + (size_t)(d.ncnln > 0 ? d.ncnln : 1) +
                                          (h->J ? jper : 0) + (h->Z ? (size_t)d.nZ : 0));
@@ -1873,7 +1875,8 @@ int ntgb_eval_host(ntgb_problem *pb, const ntgb_eval_args *h)
         const int rz = eval_host_small(pb, h, jper);
         if (rz != 1) return rz; /* 1: did not fit after all */
     }
-    long long chunk = (long long)((64ull << 20) / (per ? per : 1));
+    static const unsigned long long chunk_mb = getenv("NTG_B200_HOST_CHUNK_MB") ? strtoull(getenv("NTG_B200_HOST_CHUNK_MB"), nullptr, 10) : 192ull;
+    long long chunk = (long long)(((chunk_mb ? chunk_mb : 192ull) << 20) / (per ? per : 1));
     if (chunk < 1024) chunk = 1024;
     if (chunk > h->P) chunk = h->P;
     const int nbuf = chunk < h->P ? 2 : 1;

@@ -1014,9 +1014,15 @@ int launch_eval_small(const ntgb_launch *L)
                      ((uintptr_t)a.result & 15u) == 0; /* the peer-store variant writes (objective, violation) as one 16-byte pair */
     /* the same steady state with NPSOL's dense column-major Jacobian (single GPU) */
     const bool hot_dense = steady && a.jac_layout == NTGB_JAC_DENSE && a.npeers == 0;
-    /* the steady-state kernel exists with and without the peer stores of the fused multi-GPU
-     * gather, so that the single-GPU instantiation carries none of their code */
-    static const bool force_peers = getenv("NTG_B200_FORCE_PEERS_KERNEL") != nullptr; /* A/B: code shape vs NVLink */
+    /* the steady-state kernel exists with and without the push epilogue of the fused multi-GPU gather
+     * (a tile's result pairs collected in shared memory and stored once per tile).  The push variant
+     * is the faster one on a single GPU too, where the only destination is the local table (cfg4:
+     * 122.3 against 125.1 us), when a CTA walks several tiles; for one tile per CTA its last push sits
+     * on the critical path (cfg2 4.6 against 4.2 us).  NTG_B200_NO_PUSH_KERNEL=1 selects the other
+     * for A/B */
+    static const bool push_default = getenv("NTG_B200_NO_PUSH_KERNEL") == nullptr;
+    const long long tiles_tile_mode = (((long long)P + rows_tiles - 1) / rows_tiles + slots - 1) / slots;
+    bool force_peers = push_default && (ktiles > 0 ? ktiles > 1 : tiles_tile_mode > 1);
     using kern_t = void (*)(const ntgb_devtab, const ntgb_eval_args, int, int, int, int);
     auto pick = [&](int tile_rows) -> kern_t {
         const bool push_ok = tile_rows <= block; /* one thread per pair of a tile */
@@ -1035,6 +1041,7 @@ int launch_eval_small(const ntgb_launch *L)
         R = R_tiles;
         rows = rows_tiles;
         smem = smem_rows(rows);
+        force_peers = push_default && tiles_tile_mode > 1;
         kern = pick(rows);
         if (int rc = resident_blocks((const void *)kern, block, smem, L->max_smem_optin, &nb)) return rc;
     }

@@ -511,6 +511,12 @@ def test_alternating_batch_sizes_keep_launching(torch_cuda, port):
     h = pb.eval_host(X[:20000])
     h = pb.eval_host(X[:20000])
     assert_close(h["f"][:64], ref["f"], "chunked host path, second call")
+    # two chunks (~192 MB of results each): every row equals the device-buffer path, bit for bit
+    o = pb.eval(torch.from_numpy(X[:20000]).cuda())
+    torch.cuda.synchronize()
+    for k in ("f", "g", "result"):
+        assert np.array_equal(h[k], o[k].cpu().numpy()), f"chunked host path: {k}"
+    assert np.array_equal(h["J"].reshape(20000, -1), o["J"].cpu().numpy().reshape(20000, -1)), "chunked host path: J"
     pb.close()
 
 

@@ -454,7 +454,6 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
     const int cls = (bp == 0 ? 1 : 0) | (bp == nbps - 1 ? 2 : 0);
     double Bt[NB > 0 ? NB : 1];
     int offj[NOUT];
-#ifndef NTG_BT_LATE
     static_for<0, NOUT>([&](auto jc) {
         constexpr int j = decltype(jc)::value;
         constexpr int MD = PK::md(j);
@@ -467,7 +466,6 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
             for (int d = 0; d < MD; d++)
                 Bt[TB + k * MD + d] = (active && k < order) ? __ldg(T.Bt[j] + (size_t)(k * MD + d) * nbps + bp) : 0.0;
     });
-#endif
     const int bdim = (int)blockDim.x;
     auto rot = [&](int off) { const int t = (int)threadIdx.x - off; return t < 0 ? t + bdim : t; };
     const int tw = (int)threadIdx.x;                                   /* weights: from warp 0      */
@@ -581,20 +579,6 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
         }
     }
     for (int c = tc; c <= nC; c += bdim) cols_s[c] = use_sched ? __ldg(sched_cols + c) : c;
-#ifdef NTG_BT_LATE
-    static_for<0, NOUT>([&](auto jc) {
-        constexpr int j = decltype(jc)::value;
-        constexpr int MD = PK::md(j);
-        constexpr int TB = pk_tab_base<PK>(j);
-        const int order = T.order[j];
-        offj[j] = active ? __ldg(T.off[j] + bp) : 0;
-#pragma unroll
-        for (int k = 0; k < PK::kMaxOrd; k++)
-#pragma unroll
-            for (int d = 0; d < MD; d++)
-                Bt[TB + k * MD + d] = (active && k < order) ? __ldg(T.Bt[j] + (size_t)(k * MD + d) * nbps + bp) : 0.0;
-    });
-#endif
     if (flags & 1) {
         asm volatile("griddepcontrol.wait;" ::: "memory");
         if (ntl > 0) stage_C(p_first, pend - p_first < GR ? pend - p_first : GR, 0);

@@ -32,7 +32,7 @@ rep('        /* the barrier at the top of the next iteration separates this phas
     '        __syncthreads(); STAMP(5);\n    }')
 rep('    cp_async_wait_all();\n    if constexpr (PUSH) { /* the last tile', '    STAMP(6);\n    cp_async_wait_all();\n    if constexpr (PUSH) { /* the last tile')
 open(p, "w").write(s)
-for vdir, extra in (("stamps", []), ("stamps_late", ["-DNTG_BT_LATE"])):
+for vdir, extra in (("stamps", []),):
     out = os.path.join(ROOT, "build", "variants", vdir)
     os.makedirs(out, exist_ok=True)
     for name in ("vdp_fast", "kincar_fast"):

@@ -607,7 +607,7 @@ def kernel_source_hash(cfg: str) -> str:
     kernel (the .git directory does not travel to the GPU box, so the working tree is hashed)."""
     import hashlib
     files = ["ntg_b200/csrc/ntg_kernel_args.h", "ntg_b200/csrc/ntg_eval_kernel.cuh", "ntg_b200/csrc/ntg_eval_small.cuh",
-             "include/ntg_b200.h"]
+             "ntg_b200/csrc/ntg_small_plan.h", "include/ntg_b200.h"]
     files += {"cfg2": ["ntg_b200/packs/vdp.c"], "cfg3": ["ntg_b200/packs/kincar.c"], "cfg4": ["ntg_b200/packs/kincar.c"],
               "cfg5": ["ntg_b200/csrc/ntg_eval_cluster.cuh", "ntg_b200/csrc/ntg_eval_cluster_hot.cuh",
                        "ntg_b200/packs/syn6.c"]}[cfg]

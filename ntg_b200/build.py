@@ -304,7 +304,7 @@ def build_pack(m: PackManifest, verbose: bool = False, force: bool = False, ptxa
     core = build_core(verbose)
     wrapper = generate_wrapper(m, verbose)
     so = pack_so(m.name)
-    deps = [wrapper, os.path.abspath(m.src), core, os.path.join(CSRC, "ntg_eval_kernel.cuh"), os.path.join(CSRC, "ntg_eval_small.cuh"), os.path.join(CSRC, "ntg_eval_cluster.cuh"), os.path.join(CSRC, "ntg_eval_cluster_hot.cuh"),
+    deps = [wrapper, os.path.abspath(m.src), core, os.path.join(CSRC, "ntg_eval_kernel.cuh"), os.path.join(CSRC, "ntg_eval_small.cuh"), os.path.join(CSRC, "ntg_small_plan.h"), os.path.join(CSRC, "ntg_eval_cluster.cuh"), os.path.join(CSRC, "ntg_eval_cluster_hot.cuh"),
             os.path.join(CSRC, "ntg_kernel_args.h"), os.path.join(INCLUDE, "ntg_b200.h"),
             os.path.join(INCLUDE, "ntg.h")]
     if force or ptxas_v or _newer(so, deps):

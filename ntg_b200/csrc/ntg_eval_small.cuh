@@ -34,6 +34,7 @@
 #include <cstring>
 
 #include "ntg_eval_kernel.cuh"
+#include "ntg_small_plan.h"
 
 namespace ntgb {
 
@@ -46,38 +47,6 @@ __host__ __device__ constexpr int pk_tab_base(int j)
 }
 template <class PK>
 __host__ __device__ constexpr int pk_tab_doubles() { return pk_tab_base<PK>(PK::kNout); }
-
-struct SmallSmem {
-    int GR, nbps, S, nout, nC, segtot;
-    /* D, f and viol hold one ROW of `pitch` doubles per (band slot, problem): phase A lanes are
-     * consecutive breakpoints of one row (stride 1), phase B lanes are consecutive problems (stride
-     * pitch) and a chain walks its row with 16-byte loads.  pitch is even with pitch/2 odd, so the
-     * eight lanes of a quarter-warp hit eight different 16-byte bank groups. */
-    __host__ __device__ int pitch() const
-    {
-        int p = (nbps + 1) & ~1;
-        if (((p >> 1) & 1) == 0) p += 2;
-        return p;
-    }
-    __host__ __device__ static size_t even(size_t n) { return (n + 1) & ~(size_t)1; }
-    __host__ __device__ size_t D_off() const { return 0; }                                         /* [S][GR][pitch] */
-    __host__ __device__ size_t f_off() const { return (size_t)S * GR * pitch(); }                  /* [GR][pitch]    */
-    __host__ __device__ size_t viol_off() const { return f_off() + (size_t)GR * pitch(); }         /* [GR][pitch]    */
-    __host__ __device__ size_t DI_off() const { return viol_off() + (size_t)GR * pitch(); }        /* [GR][S]        */
-    __host__ __device__ size_t DF_off() const { return DI_off() + even((size_t)GR * S); }          /* [GR][S]        */
-    __host__ __device__ size_t cI_off() const { return DF_off() + even((size_t)GR * S); }          /* [GR]           */
-    __host__ __device__ size_t cF_off() const { return cI_off() + even(GR); }                      /* [GR]           */
-    __host__ __device__ size_t res_off() const { return cF_off() + even(GR); }                     /* [GR][2] (objective, violation) */
-    __host__ __device__ size_t dt_off() const { return res_off() + 2 * (size_t)GR; }               /* wt, Wf: [2][pitch + 2] */
-    __host__ __device__ size_t C_off() const { return dt_off() + 2 * (size_t)(pitch() + 2); }      /* [2][GR*nC]     */
-    __host__ __device__ size_t seg_off() const { return C_off() + 2 * even((size_t)GR * nC); }     /* ints, see the kernel */
-    __host__ __device__ size_t bytes() const
-    {
-        /* ints: run tables, cost run, chain table, column list; then (8-byte aligned) the peer table pointers */
-        const size_t ints = 2 * (size_t)segtot + 4 + (size_t)(nC + 1) * 10;
-        return seg_off() * 8 + ((ints + 1) & ~(size_t)1) * 4 + (NTGB_MAXPEERS + 1) * 8 + 8;
-    }
-};
 
 __device__ __forceinline__ void cp_async8(double *dst_smem, const double *src)
 {
@@ -919,76 +888,23 @@ int launch_eval_small(const ntgb_launch *L)
 {
     const ntgb_devtab &T = L->tab;
     const int nbps = T.nbps, P = L->args.P;
-    const bool wide = nbps > 256; /* one problem per round on a CTA of 512 threads (same registers per thread, one CTA per SM) */
-    int block = wide ? 512 : 256;
-    int G = block / nbps;
-    if (G > P) {
-        G = P > 0 ? P : 1;
-        int need = ((G * nbps) + 31) / 32 * 32;
-        if (need < 64) need = 64;
-        if (need < block) block = need;
-    }
+    const bool wide = nbps > 256;
     int segtot = 0;
     bool full = true;
     for (int j = 0; j < T.nout; j++) {
         segtot += T.nseg[j] + 1;
         full = full && T.order[j] == PK::kMaxOrd;
     }
-    /* R rounds per tile: enough (problem, column) chains to fill the CTA in phase B; for small
-     * batches, enough problems per tile that the whole batch is ONE wave of resident CTAs (a
-     * second, mostly empty wave would double the latency); within ~100 KB of shared memory. */
-    const int slots = (wide ? 1 : 2) * L->sm_count; /* __launch_bounds__(256, 2) / (512, 1) */
-    const int ncol = T.nC + 1;
-    auto smem_rows = [&](int rows) { return SmallSmem{rows, nbps, T.S, T.nout, T.nC, segtot}.bytes(); };
-    int R = (block + G * ncol - 1) / (G * ncol);
-    const int r_wave = (int)(((long long)P + (long long)G * slots - 1) / ((long long)G * slots));
-    if (r_wave <= 8) R = r_wave;   /* single wave */
-    const char *er = getenv("NTG_B200_ROUNDS"); /* tuning experiments */
-    if (er) R = atoi(er);
-    if (R < 1) R = 1;
-    if (R > 8) R = 8;
-    const size_t smem_cap = (size_t)(getenv("NTG_B200_SMEMCAP") ? atoi(getenv("NTG_B200_SMEMCAP")) : (wide ? 200 : 100)) * 1024;
-    while (R > 1 && smem_rows(G * R) > smem_cap) R--;
-    int rows = G * R; /* problems a tile's buffers hold */
-    /* Batches of a few tiles per CTA: whole tiles of G*R problems dealt round-robin leave some CTAs a
-     * tile more than others (8192 lane changes: 683 tiles of 12 on 296 CTAs, three for some and two
-     * for the rest; CFG-3: 228 tiles of 36 and 68 empty slots).  An EVEN split gives every CTA the same
-     * number of tiles, ktiles, and every tile P / (ktiles * grid) problems (+1 for the first few),
-     * with buffers of exactly that many rows.  Taken when it shortens the busiest CTA's critical path,
-     * counted as rounds of phase A plus passes of phase B over its (problem, column) chains (measured,
-     * lane changes of 64 breakpoints: 4096 problems 12.6 -> 10.9 us, 8192 21.4 -> 18.8, 16384 36.2 -> 34.3,
-     * 32768 65.2 -> 64.5; no difference beyond). */
-    static const bool no_even = getenv("NTG_B200_NO_EVEN_SPLIT") != nullptr; /* A/B */
-    const int R_tiles = R, rows_tiles = rows;
-    int ktiles = 0, even_grid = 0;
-    if (!no_even && !er && P >= G) {
-        const long long nt = ((long long)P + rows - 1) / rows;
-        const long long grid_t = nt < slots ? nt : slots;
-        const long long per_cta_t = (nt + grid_t - 1) / grid_t;
-        static const int even_max = getenv("NTG_B200_EVEN_MAXTILES") ? atoi(getenv("NTG_B200_EVEN_MAXTILES")) : 8; /* tuning */
-        if (per_cta_t <= even_max) {
-            const long long cand = ((long long)P + G - 1) / G;
-            const int ge = cand < slots ? (int)cand : slots;
-            const int n = (P + ge - 1) / ge; /* problems of the busiest CTA */
-            int tcap = 8 * G < block ? 8 * G : block;
-            while (tcap > 1 && smem_rows(tcap) > smem_cap) tcap--;
-            const int k = (n + tcap - 1) / tcap;
-            if (k <= 63) {
-                const long long nte = (long long)k * ge;
-                const int tmax = (int)((P + nte - 1) / nte);
-                const int Re = (tmax + G - 1) / G;
-                auto cost = [&](int t, int r) { return r + (t * ncol + block - 1) / block; };
-                /* a tie goes to the even split when some CTAs would get a tile more than others, and to whole
-                 * tiles for one tile per CTA (fewer CTAs: more of the next launch's prologues overlap) */
-                if ((long long)k * cost(tmax, Re) < per_cta_t * cost(rows, R) + (per_cta_t > 1 ? 1 : 0)) {
-                    ktiles = k;
-                    even_grid = ge;
-                    R = Re;
-                    rows = tmax;
-                }
-            }
-        }
-    }
+    /* the geometry (rounds per tile, tile rows, whole tiles or an even split): ntg_small_plan.h */
+    static const SmallPlanKnobs knobs = {getenv("NTG_B200_ROUNDS") ? atoi(getenv("NTG_B200_ROUNDS")) : 0,
+                                         getenv("NTG_B200_SMEMCAP") ? atoi(getenv("NTG_B200_SMEMCAP")) : 0,
+                                         getenv("NTG_B200_NO_EVEN_SPLIT") != nullptr,
+                                         getenv("NTG_B200_EVEN_MAXTILES") ? atoi(getenv("NTG_B200_EVEN_MAXTILES")) : 8};
+    const SmallPlan plan = plan_small_launch(P, nbps, T.S, T.nout, T.nC, segtot, L->sm_count, knobs);
+    const int block = plan.block, G = plan.G, slots = plan.slots, R_tiles = plan.R_tiles, rows_tiles = plan.rows_tiles;
+    const int even_grid = plan.even_grid;
+    int R = plan.R, rows = plan.rows, ktiles = plan.ktiles;
+    auto smem_rows = [&](int r) { return SmallSmem{r, nbps, T.S, T.nout, T.nC, segtot}.bytes(); };
     size_t smem = smem_rows(rows);
     if (smem > (size_t)L->max_smem_optin) return -1001;
     const ntgb_eval_args &a = L->args;

@@ -12,7 +12,7 @@
 
 #include <vector_types.h>
 
-#define NTGB_KERNEL_ABI 12
+#define NTGB_KERNEL_ABI 13
 #define NTGB_MAXOUT 8      /* outputs per problem the device tables can describe */
 #define NTGB_MAXORDER 20   /* PGS bsplvb work arrays: jmax = 20   */
 #define NTGB_MAXNLB 16     /* nonlinear bounds carried by value in the kernel params */

@@ -367,8 +367,6 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
     const bool wantZ = !HOT && A.Z != nullptr;
     const bool want_c = HOT || A.c != nullptr;
 
-    /* the first tile's coefficients are requested before anything else: small batches are one tile
-     * per CTA and this latency would otherwise sit behind the table loads below */
     /* tiles: GR problems each, dealt round-robin to the CTAs -- or, for a batch of a few tiles per CTA
      * (launch_eval_small), an EVEN split: CTA b owns the contiguous problems [b*P/grid, (b+1)*P/grid)
      * and walks them in tiles of GR (the launcher sizes GR so that every CTA needs the same number of
@@ -410,7 +408,7 @@ ntg_eval_small_kernel(const ntgb_devtab T, const ntgb_eval_args A, int G, int R,
      * previous launch; coefficients are read and results written after the wait.  The grid behind
      * this one may start its own prologue as soon as every CTA of this grid is resident. */
     if (flags & 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    else if (ntl > 0) stage_C(p_first, pend - p_first < GR ? pend - p_first : GR, 0);
+    else if (ntl > 0) stage_C(p_first, pend - p_first < GR ? pend - p_first : GR, 0); /* no PDL: requested first, ahead of the table loads */
 
     /* ---- once per CTA: dt, offset runs, accumulators; once per thread: its table slice ----
      * A thread's table slice is requested FIRST (it is only consumed in phase A), and the three
